@@ -1,0 +1,611 @@
+// extern "C" boundary of finufft_b200: the cufinufft_* (device pointer) and finufft_* (host
+// pointer) guru + simple entry points declared in include/b200_cufinufft.h and
+// include/b200_finufft.h, plus the introspection calls of include/b200_introspect.h.
+// Exceptions thrown by the engine become the reference's integer codes here, the convention
+// of reference include/finufft_common/safe_call.h:57-80.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+
+#include "../../include/b200_cufinufft.h"
+#include "../../include/b200_finufft.h"
+#include "../../include/b200_introspect.h"
+#include "engine.hpp"
+
+using namespace b200;
+
+namespace {
+
+constexpr uint32_t kMagic = 0xB2005EEDu;
+
+struct PlanBase {
+  uint32_t magic = kMagic;
+  bool is_float  = false;
+  bool host_api  = false;
+  virtual ~PlanBase() { magic = 0; }
+};
+
+template<class T> struct DevicePlan : PlanBase {
+  Engine<T> eng;
+  DevicePlan(int type, int dim, const int64_t *nm, int iflag, int ntr, double tol,
+             const EngineOpts &o)
+      : eng(type, dim, nm, iflag, ntr, tol, o) {
+    is_float = std::is_same<T, float>::value;
+  }
+};
+
+// Host-pointer plan: keeps device mirrors of the user's arrays.
+template<class T> struct HostPlan : DevicePlan<T> {
+  using C = typename CxOf<T>::type;
+  DevBuf<T> x, y, z, s, t, u;
+  DevBuf<C> c, fk;
+  int64_t M = 0, N = 0;
+  HostPlan(int type, int dim, const int64_t *nm, int iflag, int ntr, double tol,
+           const EngineOpts &o)
+      : DevicePlan<T>(type, dim, nm, iflag, ntr, tol, o) {
+    this->host_api = true;
+  }
+};
+
+template<class F> int guarded(F &&f) {
+  try {
+    f();
+    return 0;
+  } catch (const Failure &e) {
+    return e.code;
+  } catch (const std::bad_alloc &) {
+    return ERR_ALLOC;
+  } catch (...) {
+    return ERR_UNKNOWN_EXCEPTION;
+  }
+}
+
+void check_cuda(cudaError_t e) {
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw Failure{e == cudaErrorMemoryAllocation ? ERR_ALLOC : ERR_CUDA_FAILURE};
+  }
+}
+
+// reference src/cuda/c_interface.cpp:14-31: device API indexes with 32-bit ints
+void validate_modes_gpu(int type, int dim, const int64_t *nm) {
+  if (dim < 1 || dim > 3) throw Failure{ERR_DIM_NOTVALID};
+  if (type == 3) return;
+  if (!nm) throw Failure{ERR_INVALID_ARGUMENT};
+  int64_t tot = 1;
+  for (int d = 0; d < dim; ++d) {
+    if (nm[d] <= 0 || nm[d] > std::numeric_limits<int32_t>::max()) throw Failure{ERR_NDATA_NOTVALID};
+    tot *= nm[d];
+    if (tot > std::numeric_limits<int32_t>::max()) throw Failure{ERR_NDATA_NOTVALID};
+  }
+}
+
+EngineOpts from_gpu_opts(const cufinufft_opts *o) {
+  cufinufft_opts d;
+  if (o) d = *o;
+  else cufinufft_default_opts(&d);
+  EngineOpts e;
+  e.upsampfac        = d.upsampfac;
+  e.spreadinterponly = d.gpu_spreadinterponly;
+  e.maxbatch         = d.gpu_maxbatchsize;
+  e.device           = d.gpu_device_id;
+  e.stream           = (cudaStream_t)d.gpu_stream;
+  e.modeord          = d.modeord;
+  e.maxsub           = d.gpu_maxsubprobsize > 0 ? d.gpu_maxsubprobsize : 1024;
+  e.debug            = d.debug;
+  e.allow_eps_too_small = 1;  // the device API has no such switch; clamp and proceed
+  e.check_sigma         = 0;
+  return e;
+}
+
+EngineOpts from_host_opts(const finufft_opts *o) {
+  finufft_opts d;
+  if (o) d = *o;
+  else finufft_default_opts(&d);
+  if (d.spread_kerformula != 0) throw Failure{ERR_KERFORMULA_NOTVALID};
+  EngineOpts e;
+  e.upsampfac        = d.upsampfac;
+  e.spreadinterponly = d.spreadinterponly;
+  e.maxbatch         = d.maxbatchsize;
+  int dev            = 0;
+  check_cuda(cudaGetDevice(&dev));
+  e.device  = dev;
+  e.stream  = nullptr;
+  e.modeord = d.modeord;
+  e.maxsub  = d.spread_max_sp_size > 0 ? d.spread_max_sp_size : 1024;
+  e.debug   = d.debug;
+  e.allow_eps_too_small = d.allow_eps_too_small;
+  e.check_sigma         = 1;
+  return e;
+}
+
+template<class T>
+int gpu_makeplan(int type, int dim, const int64_t *nm, int iflag, int ntr, double tol, void **out,
+                 const cufinufft_opts *o) {
+  return guarded([&] {
+    if (!out) throw Failure{ERR_INVALID_ARGUMENT};
+    *out = nullptr;
+    validate_modes_gpu(type, dim, nm);
+    *out = new DevicePlan<T>(type, dim, nm, iflag, ntr, tol, from_gpu_opts(o));
+  });
+}
+
+template<class T> DevicePlan<T> *as_plan(void *p) {
+  auto *b = static_cast<PlanBase *>(p);
+  if (!b || b->magic != kMagic || b->is_float != std::is_same<T, float>::value)
+    throw Failure{ERR_PLAN_NOTVALID};
+  return static_cast<DevicePlan<T> *>(b);
+}
+
+template<class T>
+int gpu_setpts(void *plan, int64_t M, const T *x, const T *y, const T *z, int64_t N, const T *s,
+               const T *t, const T *u) {
+  return guarded([&] {
+    auto *p = as_plan<T>(plan);
+    if (M > std::numeric_limits<int32_t>::max()) throw Failure{ERR_NDATA_NOTVALID};
+    p->eng.setpts(M, x, y, z, N, s, t, u);
+  });
+}
+template<class T> int gpu_execute(void *plan, void *c, void *fk, bool adjoint = false) {
+  using C = typename CxOf<T>::type;
+  return guarded([&] { as_plan<T>(plan)->eng.execute((C *)c, (C *)fk, adjoint); });
+}
+template<class T> int gpu_destroy(void *plan) {
+  return guarded([&] {
+    if (!plan) throw Failure{ERR_PLAN_NOTVALID};
+    delete as_plan<T>(plan);
+  });
+}
+
+// one-shot: plan + setpts + execute + destroy (reference src/cuda/c_interface.cpp:188-218)
+template<class T>
+int gpu_simple(int dim, int type, int ntr, int64_t M, const T *x, const T *y, const T *z,
+               void *c, int iflag, T eps, int64_t m0, int64_t m1, int64_t m2, int64_t nk,
+               const T *s, const T *t, const T *u, void *fk, const cufinufft_opts *o) {
+  const int64_t nm[3] = {m0, m1, m2};
+  void *plan          = nullptr;
+  int err             = gpu_makeplan<T>(type, dim, nm, iflag, ntr, (double)eps, &plan, o);
+  if (err) return err;
+  err = gpu_setpts<T>(plan, M, x, y, z, nk, s, t, u);
+  if (!err) err = gpu_execute<T>(plan, c, fk);
+  if (!err) {
+    auto *p = static_cast<DevicePlan<T> *>(static_cast<PlanBase *>(plan));
+    if (cudaStreamSynchronize(p->eng.stream()) != cudaSuccess) err = ERR_CUDA_FAILURE;
+  }
+  gpu_destroy<T>(plan);
+  return err;
+}
+
+// ---------------------------------------------------------------- host-pointer plans
+template<class T>
+int host_makeplan(int type, int dim, const int64_t *nm, int iflag, int ntr, double tol,
+                  void **out, const finufft_opts *o) {
+  return guarded([&] {
+    if (!out) throw Failure{ERR_INVALID_ARGUMENT};
+    *out = nullptr;
+    if (type < 1 || type > 3) throw Failure{ERR_TYPE_NOTVALID};
+    if (dim < 1 || dim > 3) throw Failure{ERR_DIM_NOTVALID};
+    if (ntr < 1) throw Failure{ERR_NTRANS_NOTVALID};
+    if (type != 3) validate_modes_gpu(type, dim, nm);
+    *out = new HostPlan<T>(type, dim, nm, iflag, ntr, tol, from_host_opts(o));
+  });
+}
+template<class T> HostPlan<T> *as_host_plan(void *p) {
+  auto *q = as_plan<T>(p);
+  if (!q->host_api) throw Failure{ERR_PLAN_NOTVALID};
+  return static_cast<HostPlan<T> *>(q);
+}
+template<class T> void upload(DevBuf<T> &d, const T *h, int64_t n, cudaStream_t st) {
+  d.alloc((size_t)n);
+  if (n) check_cuda(cudaMemcpyAsync(d.p, h, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, st));
+}
+template<class T>
+int host_setpts(void *plan, int64_t M, const T *x, const T *y, const T *z, int64_t N, const T *s,
+                const T *t, const T *u) {
+  return guarded([&] {
+    auto *p = as_host_plan<T>(plan);
+    if (M < 0) throw Failure{ERR_NUM_NU_PTS_INVALID};
+    if (M > std::numeric_limits<int32_t>::max()) throw Failure{ERR_NUM_NU_PTS_INVALID};
+    DeviceGuard guard(p->eng.opts.device);
+    cudaStream_t st = p->eng.stream();
+    const int dim   = p->eng.dim;
+    upload<T>(p->x, x, M, st);
+    if (dim > 1) upload<T>(p->y, y, M, st);
+    if (dim > 2) upload<T>(p->z, z, M, st);
+    if (p->eng.type == 3) {
+      if (N < 0 || N > std::numeric_limits<int32_t>::max()) throw Failure{ERR_NUM_NU_PTS_INVALID};
+      upload<T>(p->s, s, N, st);
+      if (dim > 1) upload<T>(p->t, t, N, st);
+      if (dim > 2) upload<T>(p->u, u, N, st);
+    }
+    p->M = M;
+    p->N = N;
+    p->eng.setpts(M, p->x.p, p->y.p, p->z.p, N, p->s.p, p->t.p, p->u.p);
+  });
+}
+template<class T> int host_execute(void *plan, void *c, void *fk, bool adjoint) {
+  using C = typename CxOf<T>::type;
+  return guarded([&] {
+    auto *p = as_host_plan<T>(plan);
+    DeviceGuard guard(p->eng.opts.device);
+    cudaStream_t st     = p->eng.stream();
+    const int64_t nout  = p->eng.type == 3 ? p->N : p->eng.mode_count();
+    const size_t nc_tot = (size_t)p->M * p->eng.ntr, nk_tot = (size_t)nout * p->eng.ntr;
+    p->c.alloc(nc_tot);
+    p->fk.alloc(nk_tot);
+    const bool c_is_input = (p->eng.type != 2) != adjoint;
+    if (c_is_input) {
+      if (nc_tot) check_cuda(cudaMemcpyAsync(p->c.p, c, sizeof(C) * nc_tot, cudaMemcpyHostToDevice, st));
+    } else {
+      if (nk_tot) check_cuda(cudaMemcpyAsync(p->fk.p, fk, sizeof(C) * nk_tot, cudaMemcpyHostToDevice, st));
+    }
+    p->eng.execute(p->c.p, p->fk.p, adjoint);
+    if (c_is_input) {
+      if (nk_tot) check_cuda(cudaMemcpyAsync(fk, p->fk.p, sizeof(C) * nk_tot, cudaMemcpyDeviceToHost, st));
+    } else {
+      if (nc_tot) check_cuda(cudaMemcpyAsync(c, p->c.p, sizeof(C) * nc_tot, cudaMemcpyDeviceToHost, st));
+    }
+    check_cuda(cudaStreamSynchronize(st));
+  });
+}
+template<class T> int host_destroy(void *plan) {
+  if (!plan) return 1;  // reference src/c_interface.cpp:94-95
+  return guarded([&] { delete as_host_plan<T>(plan); });
+}
+template<class T>
+int host_simple(int dim, int type, int ntr, int64_t M, const T *x, const T *y, const T *z,
+                void *c, int iflag, T eps, int64_t m0, int64_t m1, int64_t m2, int64_t nk,
+                const T *s, const T *t, const T *u, void *fk, const finufft_opts *o) {
+  const int64_t nm[3] = {m0, m1, m2};
+  void *plan          = nullptr;
+  int err             = host_makeplan<T>(type, dim, nm, iflag, ntr, (double)eps, &plan, o);
+  if (err) return err;
+  err = host_setpts<T>(plan, M, x, y, z, nk, s, t, u);
+  if (!err) err = host_execute<T>(plan, c, fk, false);
+  host_destroy<T>(plan);
+  return err;
+}
+
+template<class T> void fill_info(DevicePlan<T> *p, b200_plan_info *out) {
+  const Engine<T> &e = p->eng;
+  out->is_float = p->is_float;
+  out->type  = e.type;
+  out->dim   = e.dim;
+  out->ntr   = e.ntr;
+  out->ns    = e.ns;
+  out->nc    = e.nc;
+  out->batch = e.batch;
+  out->sigma = e.sigma;
+  out->beta  = e.beta;
+  out->tol   = e.tol;
+  for (int d = 0; d < 3; ++d) {
+    out->nf[d]    = e.nf[d];
+    out->ms[d]    = e.ms[d];
+    out->nbins[d] = e.geom.nb[d];
+  }
+  out->M    = e.M;
+  out->nsub = e.nsub;
+}
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+void cufinufft_default_opts(cufinufft_opts *o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->upsampfac          = 0.0;   // choose (2.0)
+  o->gpu_method         = 0;
+  o->gpu_sort           = 1;
+  o->gpu_maxsubprobsize = 1024;
+  o->gpu_kerevalmeth    = 1;
+  o->gpu_device_id      = 0;
+  o->gpu_stream         = nullptr;
+}
+
+int cufinufft_makeplan(int type, int dim, const int64_t *nm, int iflag, int ntr, double eps,
+                       cufinufft_plan *plan, const cufinufft_opts *o) {
+  return gpu_makeplan<double>(type, dim, nm, iflag, ntr, eps, (void **)plan, o);
+}
+int cufinufftf_makeplan(int type, int dim, const int64_t *nm, int iflag, int ntr, float eps,
+                        cufinufftf_plan *plan, const cufinufft_opts *o) {
+  return gpu_makeplan<float>(type, dim, nm, iflag, ntr, (double)eps, (void **)plan, o);
+}
+int cufinufft_setpts(cufinufft_plan p, int64_t M, const double *x, const double *y,
+                     const double *z, int N, const double *s, const double *t, const double *u) {
+  return gpu_setpts<double>(p, M, x, y, z, N, s, t, u);
+}
+int cufinufftf_setpts(cufinufftf_plan p, int64_t M, const float *x, const float *y,
+                      const float *z, int N, const float *s, const float *t, const float *u) {
+  return gpu_setpts<float>(p, M, x, y, z, N, s, t, u);
+}
+int cufinufft_execute(cufinufft_plan p, void *c, void *fk) { return gpu_execute<double>(p, c, fk); }
+int cufinufftf_execute(cufinufftf_plan p, void *c, void *fk) { return gpu_execute<float>(p, c, fk); }
+int cufinufft_destroy(cufinufft_plan p) { return gpu_destroy<double>(p); }
+int cufinufftf_destroy(cufinufftf_plan p) { return gpu_destroy<float>(p); }
+
+#define NUL nullptr
+#define B200_CU_SIMPLE_DEF(P, R)                                                                \
+  int cufinufft##P##1d1many(int ntr, int64_t M, const R *x, const void *c, int iflag, R eps,     \
+                            int64_t ms, void *fk, const cufinufft_opts *o) {                     \
+    return gpu_simple<R>(1, 1, ntr, M, x, NUL, NUL, (void *)c, iflag, eps, ms, 1, 1, 0, NUL,     \
+                         NUL, NUL, fk, o);                                                       \
+  }                                                                                              \
+  int cufinufft##P##1d1(int64_t M, const R *x, const void *c, int iflag, R eps, int64_t ms,      \
+                        void *fk, const cufinufft_opts *o) {                                     \
+    return cufinufft##P##1d1many(1, M, x, c, iflag, eps, ms, fk, o);                             \
+  }                                                                                              \
+  int cufinufft##P##1d2many(int ntr, int64_t M, const R *x, void *c, int iflag, R eps,           \
+                            int64_t ms, const void *fk, const cufinufft_opts *o) {               \
+    return gpu_simple<R>(1, 2, ntr, M, x, NUL, NUL, c, iflag, eps, ms, 1, 1, 0, NUL, NUL, NUL,   \
+                         (void *)fk, o);                                                         \
+  }                                                                                              \
+  int cufinufft##P##1d2(int64_t M, const R *x, void *c, int iflag, R eps, int64_t ms,            \
+                        const void *fk, const cufinufft_opts *o) {                               \
+    return cufinufft##P##1d2many(1, M, x, c, iflag, eps, ms, fk, o);                             \
+  }                                                                                              \
+  int cufinufft##P##1d3many(int ntr, int64_t M, const R *x, const void *c, int iflag, R eps,     \
+                            int64_t nk, const R *s, void *fk, const cufinufft_opts *o) {         \
+    return gpu_simple<R>(1, 3, ntr, M, x, NUL, NUL, (void *)c, iflag, eps, 1, 1, 1, nk, s, NUL,  \
+                         NUL, fk, o);                                                            \
+  }                                                                                              \
+  int cufinufft##P##1d3(int64_t M, const R *x, const void *c, int iflag, R eps, int64_t nk,      \
+                        const R *s, void *fk, const cufinufft_opts *o) {                         \
+    return cufinufft##P##1d3many(1, M, x, c, iflag, eps, nk, s, fk, o);                          \
+  }                                                                                              \
+  int cufinufft##P##2d1many(int ntr, int64_t M, const R *x, const R *y, const void *c,           \
+                            int iflag, R eps, int64_t ms, int64_t mt, void *fk,                  \
+                            const cufinufft_opts *o) {                                           \
+    return gpu_simple<R>(2, 1, ntr, M, x, y, NUL, (void *)c, iflag, eps, ms, mt, 1, 0, NUL, NUL, \
+                         NUL, fk, o);                                                            \
+  }                                                                                              \
+  int cufinufft##P##2d1(int64_t M, const R *x, const R *y, const void *c, int iflag, R eps,      \
+                        int64_t ms, int64_t mt, void *fk, const cufinufft_opts *o) {             \
+    return cufinufft##P##2d1many(1, M, x, y, c, iflag, eps, ms, mt, fk, o);                      \
+  }                                                                                              \
+  int cufinufft##P##2d2many(int ntr, int64_t M, const R *x, const R *y, void *c, int iflag,      \
+                            R eps, int64_t ms, int64_t mt, const void *fk,                       \
+                            const cufinufft_opts *o) {                                           \
+    return gpu_simple<R>(2, 2, ntr, M, x, y, NUL, c, iflag, eps, ms, mt, 1, 0, NUL, NUL, NUL,    \
+                         (void *)fk, o);                                                         \
+  }                                                                                              \
+  int cufinufft##P##2d2(int64_t M, const R *x, const R *y, void *c, int iflag, R eps,            \
+                        int64_t ms, int64_t mt, const void *fk, const cufinufft_opts *o) {       \
+    return cufinufft##P##2d2many(1, M, x, y, c, iflag, eps, ms, mt, fk, o);                      \
+  }                                                                                              \
+  int cufinufft##P##2d3many(int ntr, int64_t M, const R *x, const R *y, const void *c,           \
+                            int iflag, R eps, int64_t nk, const R *s, const R *t, void *fk,      \
+                            const cufinufft_opts *o) {                                           \
+    return gpu_simple<R>(2, 3, ntr, M, x, y, NUL, (void *)c, iflag, eps, 1, 1, 1, nk, s, t, NUL, \
+                         fk, o);                                                                 \
+  }                                                                                              \
+  int cufinufft##P##2d3(int64_t M, const R *x, const R *y, const void *c, int iflag, R eps,      \
+                        int64_t nk, const R *s, const R *t, void *fk,                            \
+                        const cufinufft_opts *o) {                                               \
+    return cufinufft##P##2d3many(1, M, x, y, c, iflag, eps, nk, s, t, fk, o);                    \
+  }                                                                                              \
+  int cufinufft##P##3d1many(int ntr, int64_t M, const R *x, const R *y, const R *z,              \
+                            const void *c, int iflag, R eps, int64_t ms, int64_t mt,             \
+                            int64_t mu, void *fk, const cufinufft_opts *o) {                     \
+    return gpu_simple<R>(3, 1, ntr, M, x, y, z, (void *)c, iflag, eps, ms, mt, mu, 0, NUL, NUL,  \
+                         NUL, fk, o);                                                            \
+  }                                                                                              \
+  int cufinufft##P##3d1(int64_t M, const R *x, const R *y, const R *z, const void *c,            \
+                        int iflag, R eps, int64_t ms, int64_t mt, int64_t mu, void *fk,          \
+                        const cufinufft_opts *o) {                                               \
+    return cufinufft##P##3d1many(1, M, x, y, z, c, iflag, eps, ms, mt, mu, fk, o);               \
+  }                                                                                              \
+  int cufinufft##P##3d2many(int ntr, int64_t M, const R *x, const R *y, const R *z, void *c,     \
+                            int iflag, R eps, int64_t ms, int64_t mt, int64_t mu,                \
+                            const void *fk, const cufinufft_opts *o) {                           \
+    return gpu_simple<R>(3, 2, ntr, M, x, y, z, c, iflag, eps, ms, mt, mu, 0, NUL, NUL, NUL,     \
+                         (void *)fk, o);                                                         \
+  }                                                                                              \
+  int cufinufft##P##3d2(int64_t M, const R *x, const R *y, const R *z, void *c, int iflag,       \
+                        R eps, int64_t ms, int64_t mt, int64_t mu, const void *fk,               \
+                        const cufinufft_opts *o) {                                               \
+    return cufinufft##P##3d2many(1, M, x, y, z, c, iflag, eps, ms, mt, mu, fk, o);               \
+  }                                                                                              \
+  int cufinufft##P##3d3many(int ntr, int64_t M, const R *x, const R *y, const R *z,              \
+                            const void *c, int iflag, R eps, int64_t nk, const R *s,             \
+                            const R *t, const R *u, void *fk, const cufinufft_opts *o) {         \
+    return gpu_simple<R>(3, 3, ntr, M, x, y, z, (void *)c, iflag, eps, 1, 1, 1, nk, s, t, u, fk, \
+                         o);                                                                     \
+  }                                                                                              \
+  int cufinufft##P##3d3(int64_t M, const R *x, const R *y, const R *z, const void *c,            \
+                        int iflag, R eps, int64_t nk, const R *s, const R *t, const R *u,        \
+                        void *fk, const cufinufft_opts *o) {                                     \
+    return cufinufft##P##3d3many(1, M, x, y, z, c, iflag, eps, nk, s, t, u, fk, o);              \
+  }
+B200_CU_SIMPLE_DEF(, double)
+B200_CU_SIMPLE_DEF(f, float)
+
+// ------------------------------------------------------------------ host-pointer API
+static void host_default_opts(finufft_opts *o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->showwarn           = 1;
+  o->fftw               = 64;  // FINUFFT_FFT_DEFAULT of an FFTW build; unused here
+  o->spread_sort        = 2;
+  o->spread_kerevalmeth = 1;
+  o->spread_kerpad      = 1;
+  o->upsampfac          = 0.0;
+  o->spread_nthr_atomic = -1;
+}
+extern const int FINUFFT_FFT_DEFAULT;
+const int FINUFFT_FFT_DEFAULT = 64;  // reference include/finufft_opts.h:27
+void finufft_default_opts(finufft_opts *o) { host_default_opts(o); }
+void finufftf_default_opts(finufft_opts *o) { host_default_opts(o); }
+
+int finufft_makeplan(int type, int dim, const int64_t *nm, int iflag, int ntr, double tol,
+                     finufft_plan *plan, finufft_opts *o) {
+  return host_makeplan<double>(type, dim, nm, iflag, ntr, tol, (void **)plan, o);
+}
+int finufftf_makeplan(int type, int dim, const int64_t *nm, int iflag, int ntr, float tol,
+                      finufftf_plan *plan, finufft_opts *o) {
+  return host_makeplan<float>(type, dim, nm, iflag, ntr, (double)tol, (void **)plan, o);
+}
+int finufft_setpts(finufft_plan p, int64_t M, const double *x, const double *y, const double *z,
+                   int64_t N, const double *s, const double *t, const double *u) {
+  return host_setpts<double>(p, M, x, y, z, N, s, t, u);
+}
+int finufftf_setpts(finufftf_plan p, int64_t M, const float *x, const float *y, const float *z,
+                    int64_t N, const float *s, const float *t, const float *u) {
+  return host_setpts<float>(p, M, x, y, z, N, s, t, u);
+}
+int finufft_execute(finufft_plan p, void *c, void *fk) { return host_execute<double>(p, c, fk, false); }
+int finufftf_execute(finufftf_plan p, void *c, void *fk) { return host_execute<float>(p, c, fk, false); }
+int finufft_execute_adjoint(finufft_plan p, void *c, void *fk) {
+  return host_execute<double>(p, c, fk, true);
+}
+int finufftf_execute_adjoint(finufftf_plan p, void *c, void *fk) {
+  return host_execute<float>(p, c, fk, true);
+}
+int finufft_destroy(finufft_plan p) { return host_destroy<double>(p); }
+int finufftf_destroy(finufftf_plan p) { return host_destroy<float>(p); }
+
+#define B200_HOST_SIMPLE_DEF(P, R)                                                               \
+  int finufft##P##1d1many(int ntr, int64_t M, const R *x, const void *c, int iflag, R eps,       \
+                          int64_t ms, void *fk, finufft_opts *o) {                               \
+    return host_simple<R>(1, 1, ntr, M, x, NUL, NUL, (void *)c, iflag, eps, ms, 1, 1, 0, NUL,    \
+                          NUL, NUL, fk, o);                                                      \
+  }                                                                                              \
+  int finufft##P##1d1(int64_t M, const R *x, const void *c, int iflag, R eps, int64_t ms,        \
+                      void *fk, finufft_opts *o) {                                               \
+    return finufft##P##1d1many(1, M, x, c, iflag, eps, ms, fk, o);                               \
+  }                                                                                              \
+  int finufft##P##1d2many(int ntr, int64_t M, const R *x, void *c, int iflag, R eps,             \
+                          int64_t ms, const void *fk, finufft_opts *o) {                         \
+    return host_simple<R>(1, 2, ntr, M, x, NUL, NUL, c, iflag, eps, ms, 1, 1, 0, NUL, NUL, NUL,  \
+                          (void *)fk, o);                                                        \
+  }                                                                                              \
+  int finufft##P##1d2(int64_t M, const R *x, void *c, int iflag, R eps, int64_t ms,              \
+                      const void *fk, finufft_opts *o) {                                         \
+    return finufft##P##1d2many(1, M, x, c, iflag, eps, ms, fk, o);                               \
+  }                                                                                              \
+  int finufft##P##1d3many(int ntr, int64_t M, const R *x, const void *c, int iflag, R eps,       \
+                          int64_t nk, const R *s, void *fk, finufft_opts *o) {                   \
+    return host_simple<R>(1, 3, ntr, M, x, NUL, NUL, (void *)c, iflag, eps, 1, 1, 1, nk, s, NUL, \
+                          NUL, fk, o);                                                           \
+  }                                                                                              \
+  int finufft##P##1d3(int64_t M, const R *x, const void *c, int iflag, R eps, int64_t nk,        \
+                      const R *s, void *fk, finufft_opts *o) {                                   \
+    return finufft##P##1d3many(1, M, x, c, iflag, eps, nk, s, fk, o);                            \
+  }                                                                                              \
+  int finufft##P##2d1many(int ntr, int64_t M, const R *x, const R *y, const void *c, int iflag,  \
+                          R eps, int64_t ms, int64_t mt, void *fk, finufft_opts *o) {            \
+    return host_simple<R>(2, 1, ntr, M, x, y, NUL, (void *)c, iflag, eps, ms, mt, 1, 0, NUL,     \
+                          NUL, NUL, fk, o);                                                      \
+  }                                                                                              \
+  int finufft##P##2d1(int64_t M, const R *x, const R *y, const void *c, int iflag, R eps,        \
+                      int64_t ms, int64_t mt, void *fk, finufft_opts *o) {                       \
+    return finufft##P##2d1many(1, M, x, y, c, iflag, eps, ms, mt, fk, o);                        \
+  }                                                                                              \
+  int finufft##P##2d2many(int ntr, int64_t M, const R *x, const R *y, void *c, int iflag,        \
+                          R eps, int64_t ms, int64_t mt, const void *fk, finufft_opts *o) {      \
+    return host_simple<R>(2, 2, ntr, M, x, y, NUL, c, iflag, eps, ms, mt, 1, 0, NUL, NUL, NUL,   \
+                          (void *)fk, o);                                                        \
+  }                                                                                              \
+  int finufft##P##2d2(int64_t M, const R *x, const R *y, void *c, int iflag, R eps, int64_t ms,  \
+                      int64_t mt, const void *fk, finufft_opts *o) {                             \
+    return finufft##P##2d2many(1, M, x, y, c, iflag, eps, ms, mt, fk, o);                        \
+  }                                                                                              \
+  int finufft##P##2d3many(int ntr, int64_t M, const R *x, const R *y, const void *c, int iflag,  \
+                          R eps, int64_t nk, const R *s, const R *t, void *fk,                   \
+                          finufft_opts *o) {                                                     \
+    return host_simple<R>(2, 3, ntr, M, x, y, NUL, (void *)c, iflag, eps, 1, 1, 1, nk, s, t,     \
+                          NUL, fk, o);                                                           \
+  }                                                                                              \
+  int finufft##P##2d3(int64_t M, const R *x, const R *y, const void *c, int iflag, R eps,        \
+                      int64_t nk, const R *s, const R *t, void *fk, finufft_opts *o) {           \
+    return finufft##P##2d3many(1, M, x, y, c, iflag, eps, nk, s, t, fk, o);                      \
+  }                                                                                              \
+  int finufft##P##3d1many(int ntr, int64_t M, const R *x, const R *y, const R *z,                \
+                          const void *c, int iflag, R eps, int64_t ms, int64_t mt, int64_t mu,   \
+                          void *fk, finufft_opts *o) {                                           \
+    return host_simple<R>(3, 1, ntr, M, x, y, z, (void *)c, iflag, eps, ms, mt, mu, 0, NUL, NUL, \
+                          NUL, fk, o);                                                           \
+  }                                                                                              \
+  int finufft##P##3d1(int64_t M, const R *x, const R *y, const R *z, const void *c, int iflag,   \
+                      R eps, int64_t ms, int64_t mt, int64_t mu, void *fk, finufft_opts *o) {    \
+    return finufft##P##3d1many(1, M, x, y, z, c, iflag, eps, ms, mt, mu, fk, o);                 \
+  }                                                                                              \
+  int finufft##P##3d2many(int ntr, int64_t M, const R *x, const R *y, const R *z, void *c,       \
+                          int iflag, R eps, int64_t ms, int64_t mt, int64_t mu,                  \
+                          const void *fk, finufft_opts *o) {                                     \
+    return host_simple<R>(3, 2, ntr, M, x, y, z, c, iflag, eps, ms, mt, mu, 0, NUL, NUL, NUL,    \
+                          (void *)fk, o);                                                        \
+  }                                                                                              \
+  int finufft##P##3d2(int64_t M, const R *x, const R *y, const R *z, void *c, int iflag,         \
+                      R eps, int64_t ms, int64_t mt, int64_t mu, const void *fk,                 \
+                      finufft_opts *o) {                                                         \
+    return finufft##P##3d2many(1, M, x, y, z, c, iflag, eps, ms, mt, mu, fk, o);                 \
+  }                                                                                              \
+  int finufft##P##3d3many(int ntr, int64_t M, const R *x, const R *y, const R *z,                \
+                          const void *c, int iflag, R eps, int64_t nk, const R *s, const R *t,   \
+                          const R *u, void *fk, finufft_opts *o) {                               \
+    return host_simple<R>(3, 3, ntr, M, x, y, z, (void *)c, iflag, eps, 1, 1, 1, nk, s, t, u,    \
+                          fk, o);                                                                \
+  }                                                                                              \
+  int finufft##P##3d3(int64_t M, const R *x, const R *y, const R *z, const void *c, int iflag,   \
+                      R eps, int64_t nk, const R *s, const R *t, const R *u, void *fk,           \
+                      finufft_opts *o) {                                                         \
+    return finufft##P##3d3many(1, M, x, y, z, c, iflag, eps, nk, s, t, u, fk, o);                \
+  }
+B200_HOST_SIMPLE_DEF(, double)
+B200_HOST_SIMPLE_DEF(f, float)
+
+// ------------------------------------------------------------------ introspection
+int b200_get_plan_info(void *plan, b200_plan_info *out) {
+  return guarded([&] {
+    auto *b = static_cast<PlanBase *>(plan);
+    if (!b || b->magic != kMagic || !out) throw Failure{ERR_PLAN_NOTVALID};
+    if (b->is_float) fill_info<float>(as_plan<float>(plan), out);
+    else fill_info<double>(as_plan<double>(plan), out);
+  });
+}
+int b200_get_sort_permutation(void *plan, uint32_t *host_out) {
+  return guarded([&] {
+    auto *b = static_cast<PlanBase *>(plan);
+    if (!b || b->magic != kMagic) throw Failure{ERR_PLAN_NOTVALID};
+    if (b->is_float) {
+      DeviceGuard g(as_plan<float>(plan)->eng.opts.device);
+      as_plan<float>(plan)->eng.copy_sort_to_host(host_out);
+    } else {
+      DeviceGuard g(as_plan<double>(plan)->eng.opts.device);
+      as_plan<double>(plan)->eng.copy_sort_to_host(host_out);
+    }
+  });
+}
+int b200_get_window_table(void *plan, void *host_out) {
+  return guarded([&] {
+    auto *b = static_cast<PlanBase *>(plan);
+    if (!b || b->magic != kMagic) throw Failure{ERR_PLAN_NOTVALID};
+    if (b->is_float) {
+      auto &c = as_plan<float>(plan)->eng.coef;
+      std::memcpy(host_out, c.data(), c.size() * sizeof(float));
+    } else {
+      auto &c = as_plan<double>(plan)->eng.coef;
+      std::memcpy(host_out, c.data(), c.size() * sizeof(double));
+    }
+  });
+}
+int b200_get_phihat(void *plan, int d, void *host_out) {
+  return guarded([&] {
+    auto *b = static_cast<PlanBase *>(plan);
+    if (!b || b->magic != kMagic || d < 0 || d > 2) throw Failure{ERR_PLAN_NOTVALID};
+    if (b->is_float) {
+      DeviceGuard g(as_plan<float>(plan)->eng.opts.device);
+      as_plan<float>(plan)->eng.copy_phihat_to_host(d, (float *)host_out);
+    } else {
+      DeviceGuard g(as_plan<double>(plan)->eng.opts.device);
+      as_plan<double>(plan)->eng.copy_phihat_to_host(d, (double *)host_out);
+    }
+  });
+}
+const char *b200_version(void) { return "finufft_b200 0.1 sm_100a"; }
+
+}  // extern "C"

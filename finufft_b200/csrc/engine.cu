@@ -1,0 +1,329 @@
+// Plan object: makeplan / setpts / execute for types 1 and 2 (type 3 lives in type3.cu).
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <limits>
+
+#include "planmath.hpp"
+#include "spreadinterp.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ small utilities
+static void cuda_check(cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return;
+  fprintf(stderr, "[finufft_b200] CUDA error in %s: %s\n", what, cudaGetErrorString(e));
+  cudaGetLastError();  // clear
+  throw Failure{e == cudaErrorMemoryAllocation ? ERR_ALLOC : ERR_CUDA_FAILURE};
+}
+#define CU(x) cuda_check((x), #x)
+
+template<class T> void DevBuf<T>::alloc(size_t count) {
+  if (count <= n && p) return;
+  release();
+  if (count == 0) return;
+  CU(cudaMalloc((void **)&p, count * sizeof(T)));
+  n = count;
+}
+template<class T> void DevBuf<T>::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  n = 0;
+}
+template struct DevBuf<float>;
+template struct DevBuf<double>;
+template struct DevBuf<float2>;
+template struct DevBuf<double2>;
+template struct DevBuf<uint32_t>;
+
+DeviceGuard::DeviceGuard(int dev) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || dev < 0 || dev >= count) {
+    cudaGetLastError();
+    throw Failure{ERR_CUDA_FAILURE};
+  }
+  CU(cudaGetDevice(&prev));
+  if (prev != dev) CU(cudaSetDevice(dev));
+  else prev = -1;
+}
+DeviceGuard::~DeviceGuard() {
+  if (prev >= 0) cudaSetDevice(prev);
+}
+
+template<class T> static cufftType fft_kind();
+template<> cufftType fft_kind<float>() { return CUFFT_C2C; }
+template<> cufftType fft_kind<double>() { return CUFFT_Z2Z; }
+static void fft_exec(cufftHandle h, float2 *d, int dir) {
+  if (cufftExecC2C(h, d, d, dir) != CUFFT_SUCCESS) throw Failure{ERR_CUDA_FAILURE};
+}
+static void fft_exec(cufftHandle h, double2 *d, int dir) {
+  if (cufftExecZ2Z(h, d, d, dir) != CUFFT_SUCCESS) throw Failure{ERR_CUDA_FAILURE};
+}
+
+// ------------------------------------------------------------------ makeplan
+template<class T>
+Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr_, double tol_,
+                  const EngineOpts &o)
+    : type(type_), dim(dim_), ntr(ntr_), sign(iflag >= 0 ? 1 : -1), opts(o) {
+  if (type < 1 || type > 3) throw Failure{ERR_TYPE_NOTVALID};
+  if (dim < 1 || dim > 3) throw Failure{ERR_DIM_NOTVALID};
+  if (ntr < 1) throw Failure{ERR_NTRANS_NOTVALID};
+  DeviceGuard guard(opts.device);
+  tol   = tol_;
+  sigma = opts.upsampfac == 0.0 ? 2.0 : opts.upsampfac;
+  batch = opts.maxbatch > 0 ? std::min(opts.maxbatch, ntr) : std::min(ntr, 8);
+  if (opts.maxsub < 32) opts.maxsub = 32;
+  plan_kernel();
+  if (type != 3) {
+    for (int d = 0; d < dim; ++d) ms[d] = nmodes[d];
+    plan_grid();
+  }
+}
+
+template<class T> Engine<T>::~Engine() {
+  if (have_fft_) cufftDestroy(fft_);
+}
+
+template<class T> void Engine<T>::plan_kernel() {
+  constexpr bool is_f = std::is_same<T, float>::value;
+  double tol_used;
+  int err = choose_kernel(tol, dim, type, sigma, is_f, opts.allow_eps_too_small != 0, ns, beta,
+                          tol_used);
+  if (err) throw Failure{err};
+  tol = tol_used;
+  err = build_horner_table<T>(ns, beta, (T)tol, coef, nc);
+  if (err) throw Failure{err};
+  if (opts.debug)
+    printf("[finufft_b200] type %d dim %d: sigma=%.3g ns=%d beta=%.6g nc=%d\n", type, dim, sigma,
+           ns, beta, nc);
+}
+
+// fine grid, window Fourier series, cuFFT plan, bin geometry (types 1/2; type 3 calls this
+// from setpts once the grid is known)
+template<class T> void Engine<T>::plan_grid() {
+  int64_t total = 1;
+  for (int d = 0; d < dim; ++d) {
+    if (opts.spreadinterponly) nf[d] = ms[d];
+    else if (type != 3) {
+      nf[d] = fine_grid_size(sigma, ms[d], ns);
+      if (nf[d] < 0) throw Failure{ERR_MAXNALLOC};
+    }
+    total *= nf[d];
+    if (nf[d] > std::numeric_limits<int32_t>::max()) throw Failure{ERR_NDATA_NOTVALID};
+  }
+  if (total > std::numeric_limits<int32_t>::max()) throw Failure{ERR_NDATA_NOTVALID};
+  for (int d = 0; d < 3; ++d) {
+    geom.nf[d]   = (int)nf[d];
+    geom.nf_t[d] = (T)nf[d];
+  }
+  const double bs[3] = {(double)kBinX, (double)kBinY, (double)kBinZ};
+  uint64_t nbins = 1;
+  for (int d = 0; d < 3; ++d) {
+    geom.nb[d] = d < dim ? (int)(int64_t)((double)geom.nf_t[d] / bs[d] + 1) : 1;
+    nbins *= (uint64_t)geom.nb[d];
+  }
+  if (nbins > 0x7fffffffull) throw Failure{ERR_NDATA_NOTVALID};
+  geom.nbins = (uint32_t)nbins;
+  if (opts.spreadinterponly) return;
+
+  cudaStream_t st = opts.stream;
+  for (int d = 0; d < dim; ++d) {
+    phihat_[d].alloc(nf[d] / 2 + 1);
+    FseriesNodes nodes;
+    nodes.q = fseries_nodes<T>(ns, nc, coef.data(), nodes.z, nodes.f);
+    launch_fseries<T>(nf[d], nodes, phihat_[d].p, st);
+  }
+  CU(cudaGetLastError());
+  fw_.alloc((size_t)total * batch);
+  if (have_fft_) {
+    cufftDestroy(fft_);
+    have_fft_ = false;
+  }
+  int n[3];
+  for (int d = 0; d < dim; ++d) n[d] = (int)nf[dim - 1 - d];  // slowest first
+  if (cufftPlanMany(&fft_, dim, n, nullptr, 1, (int)total, nullptr, 1, (int)total, fft_kind<T>(),
+                    batch) != CUFFT_SUCCESS)
+    throw Failure{ERR_CUDA_FAILURE};
+  have_fft_ = true;
+  if (cufftSetStream(fft_, st) != CUFFT_SUCCESS) throw Failure{ERR_CUDA_FAILURE};
+}
+
+// ------------------------------------------------------------------ setpts
+template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z) {
+  cudaStream_t st = opts.stream;
+  const uint32_t m = (uint32_t)M;
+  xs_.alloc(M);
+  if (dim > 1) ys_.alloc(M);
+  if (dim > 2) zs_.alloc(M);
+  sidx_.alloc(M);
+  binstart_.alloc((size_t)geom.nbins + 1);
+  DevBuf<uint32_t> keys_a, keys_b, vals_b, hist, scan_tmp, nsubs, substart;
+  keys_a.alloc(M);
+  keys_b.alloc(M);
+  vals_b.alloc(M);
+  hist.alloc(256 * (size_t)kRadixMaxBlocks + 1);
+  const size_t scan_n = std::max<size_t>(geom.nbins + 1, 256 * (size_t)kRadixMaxBlocks + 1);
+  scan_tmp.alloc(scan_n / 4096 + 8);
+
+  launch_bin_keys<T>(dim, x, y, z, m, geom, keys_a.p, st);
+  int nbits = 0;
+  while ((1ull << nbits) < (uint64_t)geom.nbins) ++nbits;
+  const int which = radix_sort_pairs(keys_a.p, keys_b.p, sidx_.p, vals_b.p, m, nbits, hist.p,
+                                     scan_tmp.p, st);
+  const uint32_t *sorted_keys = which ? keys_b.p : keys_a.p;
+  if (which && M) {  // result landed in the scratch value buffer
+    CU(cudaMemcpyAsync(sidx_.p, vals_b.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToDevice, st));
+  }
+  launch_bin_bounds(sorted_keys, m, geom.nbins, binstart_.p, st);
+  launch_gather_coords<T>(dim, x, y, z, sidx_.p, m, xs_.p, ys_.p, zs_.p, st);
+
+  // subproblem list: every bin in chunks of at most maxsub points
+  nsubs.alloc(geom.nbins);
+  substart.alloc((size_t)geom.nbins + 1);
+  launch_sub_count(binstart_.p, geom.nbins, (uint32_t)opts.maxsub, nsubs.p, st);
+  exclusive_scan_u32(nsubs.p, substart.p, geom.nbins, scan_tmp.p, st);
+  uint32_t total = 0;
+  CU(cudaMemcpyAsync(&total, substart.p + geom.nbins, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                     st));
+  CU(cudaStreamSynchronize(st));
+  nsub = total;
+  sub_bin_.alloc(std::max<uint32_t>(nsub, 1));
+  sub_off_.alloc(std::max<uint32_t>(nsub, 1));
+  if (nsub)
+    launch_sub_fill(binstart_.p, substart.p, geom.nbins, (uint32_t)opts.maxsub, sub_bin_.p,
+                    sub_off_.p, st);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));  // scratch buffers are freed on return
+}
+
+template<class T>
+void Engine<T>::setpts(int64_t M_, const T *x, const T *y, const T *z, int64_t N, const T *s,
+                       const T *t, const T *u) {
+  DeviceGuard guard(opts.device);
+  if (M_ < 0) throw Failure{ERR_NUM_NU_PTS_INVALID};
+  if (M_ > std::numeric_limits<int32_t>::max()) throw Failure{ERR_NDATA_NOTVALID};
+  if (type == 3) {
+    setpts_type3(M_, x, y, z, N, s, t, u);
+    return;
+  }
+  M = M_;
+  if (opts.check_sigma) {  // include/finufft/setpts.hpp:29-53
+    const double eps  = std::numeric_limits<T>::epsilon();
+    const double glen = (double)*std::max_element(nf, nf + dim);
+    const bool floor_ = tol <= 0.5 * 0.48 * eps * glen;
+    if ((floor_ || least_sigma(tol, dim, ns, eps, glen) > sigma) && !opts.allow_eps_too_small)
+      throw Failure{ERR_EPS_TOO_SMALL};
+  }
+  for (int d = 0; d < dim; ++d)
+    if (nf[d] < 2 * ns) throw Failure{ERR_SPREAD_BOX_SMALL};
+  sort_points(x, y, z);
+}
+
+// ------------------------------------------------------------------ execute
+template<class T> void Engine<T>::run_spread(const C *c, C *fw) {
+  if (nsub == 0) return;
+  PointSet<T> pts{xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, sub_bin_.p, sub_off_.p, nsub,
+                  (uint32_t)opts.maxsub};
+  cudaError_t e;
+  if (dim == 1)
+    e = launch_spreadinterp<T, 1>(true, ns, pts, geom, nc, coef.data(), c, nullptr, fw, opts.stream);
+  else if (dim == 2)
+    e = launch_spreadinterp<T, 2>(true, ns, pts, geom, nc, coef.data(), c, nullptr, fw, opts.stream);
+  else
+    e = launch_spreadinterp<T, 3>(true, ns, pts, geom, nc, coef.data(), c, nullptr, fw, opts.stream);
+  if (e == cudaErrorInvalidConfiguration) throw Failure{ERR_INSUFFICIENT_SHMEM};
+  CU(e);
+}
+template<class T> void Engine<T>::run_interp(C *c, const C *fw) {
+  if (nsub == 0) return;
+  PointSet<T> pts{xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, sub_bin_.p, sub_off_.p, nsub,
+                  (uint32_t)opts.maxsub};
+  cudaError_t e;
+  C *fwm = const_cast<C *>(fw);
+  if (dim == 1)
+    e = launch_spreadinterp<T, 1>(false, ns, pts, geom, nc, coef.data(), nullptr, c, fwm, opts.stream);
+  else if (dim == 2)
+    e = launch_spreadinterp<T, 2>(false, ns, pts, geom, nc, coef.data(), nullptr, c, fwm, opts.stream);
+  else
+    e = launch_spreadinterp<T, 3>(false, ns, pts, geom, nc, coef.data(), nullptr, c, fwm, opts.stream);
+  if (e == cudaErrorInvalidConfiguration) throw Failure{ERR_INSUFFICIENT_SHMEM};
+  CU(e);
+}
+
+// NU strengths -> modes: spread, FFT, deconvolve (include/finufft/execute.hpp:376-417, type 1)
+template<class T> void Engine<T>::spread_path(C *c, C *fk, int fsign) {
+  cudaStream_t st    = opts.stream;
+  const int64_t G    = grid_cells(), Nm = mode_count();
+  ModeGeom<T> mg;
+  for (int d = 0; d < 3; ++d) {
+    mg.ms[d] = (int)ms[d];
+    mg.nf[d] = (int)nf[d];
+    mg.ph[d] = phihat_[d].p;
+  }
+  mg.modeord = opts.modeord;
+  for (int b0 = 0; b0 < ntr; b0 += batch) {
+    const int nb = std::min(batch, ntr - b0);
+    C *grid      = opts.spreadinterponly ? fk + (int64_t)b0 * Nm : fw_.p;
+    CU(cudaMemsetAsync(grid, 0, sizeof(C) * (size_t)G * nb, st));
+    for (int i = 0; i < nb; ++i) run_spread(c + (int64_t)(b0 + i) * M, grid + (int64_t)i * G);
+    if (opts.spreadinterponly) continue;
+    fft_exec(fft_, fw_.p, fsign);
+    launch_grid_to_modes<T>(dim, nb, fw_.p, fk + (int64_t)b0 * Nm, mg, st);
+  }
+  CU(cudaGetLastError());
+}
+
+// modes -> NU values: amplify + zero-pad, FFT, interpolate (type 2)
+template<class T> void Engine<T>::interp_path(C *c, C *fk, int fsign) {
+  cudaStream_t st    = opts.stream;
+  const int64_t G    = grid_cells(), Nm = mode_count();
+  ModeGeom<T> mg;
+  for (int d = 0; d < 3; ++d) {
+    mg.ms[d] = (int)ms[d];
+    mg.nf[d] = (int)nf[d];
+    mg.ph[d] = phihat_[d].p;
+  }
+  mg.modeord = opts.modeord;
+  for (int b0 = 0; b0 < ntr; b0 += batch) {
+    const int nb  = std::min(batch, ntr - b0);
+    const C *grid = fw_.p;
+    if (opts.spreadinterponly) grid = fk + (int64_t)b0 * Nm;
+    else {
+      launch_modes_to_grid<T>(dim, nb, fk + (int64_t)b0 * Nm, fw_.p, mg, st);
+      fft_exec(fft_, fw_.p, fsign);
+    }
+    for (int i = 0; i < nb; ++i) run_interp(c + (int64_t)(b0 + i) * M, grid + (int64_t)i * G);
+  }
+  CU(cudaGetLastError());
+}
+
+template<class T> void Engine<T>::execute(C *c, C *fk, bool adjoint) {
+  DeviceGuard guard(opts.device);
+  if (type == 3) {
+    if (adjoint) throw Failure{ERR_TYPE_NOTVALID};
+    exec_type3(c, fk);
+    return;
+  }
+  const bool spreading = (type == 1) != adjoint;
+  const int fsign      = adjoint ? -sign : sign;
+  if (spreading) spread_path(c, fk, fsign);
+  else interp_path(c, fk, fsign);
+}
+
+template<class T> void Engine<T>::copy_sort_to_host(uint32_t *out) const {
+  if (M == 0) return;
+  cudaStreamSynchronize(opts.stream);
+  cuda_check(cudaMemcpy(out, sidx_.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToHost), "copy sort");
+}
+template<class T> void Engine<T>::copy_phihat_to_host(int d, T *out) const {
+  cudaStreamSynchronize(opts.stream);
+  cuda_check(cudaMemcpy(out, phihat_[d].p, sizeof(T) * (nf[d] / 2 + 1), cudaMemcpyDeviceToHost),
+             "copy phihat");
+}
+
+template class Engine<float>;
+template class Engine<double>;
+
+}  // namespace b200

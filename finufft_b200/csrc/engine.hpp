@@ -1,0 +1,111 @@
+// The plan object behind the C ABI: owns every device buffer of one NUFFT plan and drives the
+// hot path  setpts (fold-rescale + bin sort) -> spread | interp -> cuFFT -> deconvolve.
+//
+// Mirrors the guru sequence of the reference (makeplan / setpts / execute / destroy):
+//   CPU  include/finufft/makeplan.hpp:317-465, setpts.hpp:107-321, execute.hpp:318-563
+//   GPU  src/cuda/makeplan.cu:223-398, src/cuda/setpts.cu:25-75, src/cuda/execute.cu:106-271
+// but is a different design: one sort that is bit-identical to the CPU library's, coordinates
+// gathered once into sorted order at setpts, fine grid and cuFFT plan kept in the plan, type-2
+// zero-padding fused into the amplify kernel, warp-private shared-memory tiles instead of
+// shared-memory atomics.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+
+#include <memory>
+#include <vector>
+
+#include "devmath.cuh"
+#include "errors.hpp"
+#include "gridops.cuh"
+#include "sort.cuh"
+
+namespace b200 {
+
+struct EngineOpts {
+  double upsampfac     = 0.0;  // 0 = choose (2.0)
+  int spreadinterponly = 0;
+  int maxbatch         = 0;    // 0 = min(ntr, 8)
+  int device           = 0;
+  cudaStream_t stream  = nullptr;
+  int modeord          = 0;
+  int maxsub           = 1024;  // most points one warp takes from one bin
+  int debug            = 0;
+  int allow_eps_too_small = 1;
+  int check_sigma      = 0;     // host (finufft_*) entry points apply the CPU feasibility rule
+};
+
+template<class T> struct DevBuf {
+  T *p     = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf &)            = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void alloc(size_t count);
+  void release();
+};
+
+struct DeviceGuard {  // make the plan's device current for the duration of a call
+  int prev = -1;
+  explicit DeviceGuard(int dev);
+  ~DeviceGuard();
+};
+
+template<class T> class Engine {
+ public:
+  using C = typename CxOf<T>::type;
+  Engine(int type, int dim, const int64_t *nmodes, int iflag, int ntr, double tol,
+         const EngineOpts &o);
+  ~Engine();
+  // all pointers are device pointers on opts.device
+  void setpts(int64_t M, const T *x, const T *y, const T *z, int64_t N, const T *s, const T *t,
+              const T *u);
+  void execute(C *c, C *fk, bool adjoint);
+
+  // ---- introspection (tests, benches) ----
+  int type, dim, ntr, sign;
+  EngineOpts opts;
+  int ns = 0, nc = 0;
+  double beta = 0, sigma = 0, tol = 0;
+  int64_t ms[3] = {1, 1, 1};
+  int64_t nf[3] = {1, 1, 1};
+  int64_t M = 0, nk = 0;
+  std::vector<T> coef;  // nc x ns, host copy
+  GridGeom<T> geom{};
+  uint32_t nsub = 0;
+  int batch = 1;
+  int64_t grid_cells() const { return nf[0] * nf[1] * nf[2]; }
+  int64_t mode_count() const { return ms[0] * ms[1] * ms[2]; }
+  void copy_sort_to_host(uint32_t *out) const;
+  void copy_phihat_to_host(int d, T *out) const;
+  cudaStream_t stream() const { return opts.stream; }
+
+ private:
+  void plan_kernel();
+  void plan_grid();
+  void sort_points(const T *x, const T *y, const T *z);
+  void run_spread(const C *c, C *fw);
+  void run_interp(C *c, const C *fw);
+  void spread_path(C *c, C *fk, int fsign);
+  void interp_path(C *c, C *fk, int fsign);
+  void exec_type3(C *c, C *fk);
+  void setpts_type3(int64_t M, const T *x, const T *y, const T *z, int64_t N, const T *s,
+                    const T *t, const T *u);
+
+  DevBuf<T> phihat_[3];
+  DevBuf<C> fw_;
+  cufftHandle fft_ = 0;
+  bool have_fft_   = false;
+  // point state
+  DevBuf<T> xs_, ys_, zs_;
+  DevBuf<uint32_t> sidx_, binstart_, sub_bin_, sub_off_;
+  // type 3
+  DevBuf<T> xp_[3], sp_[3];
+  DevBuf<C> prephase_, deconv_, cp_;
+  std::unique_ptr<Engine<T>> inner_;
+  T t3C_[3] = {0, 0, 0}, t3D_[3] = {0, 0, 0}, t3h_[3] = {0, 0, 0}, t3gam_[3] = {1, 1, 1};
+};
+
+}  // namespace b200

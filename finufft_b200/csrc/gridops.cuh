@@ -1,0 +1,35 @@
+// Declarations for the uniform-grid kernels (gridops.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "devmath.cuh"
+
+namespace b200 {
+
+template<class T> struct ModeGeom {
+  int ms[3];        // modes per dim (1 for unused dims)
+  int nf[3];        // fine grid per dim
+  int modeord;      // 0: ascending k, 1: FFT order
+  const T *ph[3];   // window Fourier series, indices 0..nf/2, device pointers
+};
+
+struct FseriesNodes {
+  int q;
+  double z[100];
+  double f[100];
+};
+
+template<class T>
+void launch_grid_to_modes(int dim, int batch, const typename CxOf<T>::type *fw,
+                          typename CxOf<T>::type *fk, const ModeGeom<T> &g, cudaStream_t st);
+template<class T>
+void launch_modes_to_grid(int dim, int batch, const typename CxOf<T>::type *fk,
+                          typename CxOf<T>::type *fw, const ModeGeom<T> &g, cudaStream_t st);
+template<class T>
+void launch_fseries(int64_t nf, const FseriesNodes &nodes, T *out, cudaStream_t st);
+template<class T>
+void launch_cmul(int batch, const typename CxOf<T>::type *a, const typename CxOf<T>::type *b,
+                 typename CxOf<T>::type *out, int64_t n, int conj_b, cudaStream_t st);
+
+}  // namespace b200

@@ -1,0 +1,325 @@
+// Host-side plan-time mathematics (see planmath.hpp for the behavioural spec citations).
+#include "planmath.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+#include "errors.hpp"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ width and shape
+static double aliasing_prefactor(int dim, int type) {
+  // tol ~ prefactor * exp(-(ns-1) pi sqrt(1-1/sigma)); empirical constants of the reference
+  // (src/common/kernel.cpp:60-77): 0.18 in 1D, x1.4 per extra dimension, x1.4 for type 3.
+  double f = 0.18;
+  for (int d = 1; d < dim; ++d) f *= 1.4;
+  if (type == 3) f *= 1.4;
+  return f;
+}
+
+int choose_kernel(double tol, int dim, int type, double sigma, bool is_float, bool allow_small,
+                  int &ns, double &beta, double &tol_used) {
+  if (!(sigma > 1.0)) return ERR_UPSAMPFAC_TOO_SMALL;
+  // tolerance is held in the plan's working precision (makeplan.hpp:154-162)
+  const double eps = is_float ? (double)std::numeric_limits<float>::epsilon()
+                              : std::numeric_limits<double>::epsilon();
+  double t = is_float ? (double)(float)tol : tol;
+  if (t < eps) {
+    if (!allow_small) return ERR_EPS_TOO_SMALL;
+    t = eps;
+  }
+  const int cap = is_float ? kMaxNsF32 : kMaxNsF64;
+  const double rate = kPi * std::sqrt(1.0 - 1.0 / sigma);
+  const int ideal   = (int)std::ceil(std::log(aliasing_prefactor(dim, type) / t) / rate + 1.0);
+  if (ideal > cap && !allow_small) return ERR_EPS_TOO_SMALL;
+  int w = std::min(std::max(ideal, 2), cap);
+  if (is_float && sigma < 1.4) w = std::min(w, 8);  // single-precision cancellation guard
+  ns       = w;
+  beta     = kPi * w * (1.0 - 0.5 / sigma) - 0.05;  // prolate bandwidth, cutoff minus 0.05
+  tol_used = t;
+  return 0;
+}
+
+// ------------------------------------------------------------------ prolate window
+// psi_0^c expanded in normalised even Legendre functions Pbar_k = sqrt(k+1/2) P_k, k=0,2,4,..:
+// (A - chi I) b = 0 with A symmetric tridiagonal
+//   A[k,k]   = k(k+1) + c^2 (2k(k+1)-1) / ((2k+3)(2k-1))
+//   A[k,k+2] = c^2 (k+2)(k+1) / ((2k+3) sqrt((2k+1)(2k+5)))
+// psi_0 belongs to the smallest eigenvalue chi_0.
+Prolate0::Prolate0(double c) {
+  const int K = 40 + (int)std::ceil(std::abs(c));
+  std::vector<double> d(K), e(K, 0.0);
+  const double c2 = c * c;
+  for (int j = 0; j < K; ++j) {
+    const double k = 2.0 * j;
+    d[j] = k * (k + 1.0) + c2 * (2.0 * k * (k + 1.0) - 1.0) / ((2.0 * k + 3.0) * (2.0 * k - 1.0));
+    e[j] = c2 * (k + 2.0) * (k + 1.0) /
+           ((2.0 * k + 3.0) * std::sqrt((2.0 * k + 1.0) * (2.0 * k + 5.0)));  // couples j, j+1
+  }
+  // Gershgorin bracket, then bisection on the Sturm count for the smallest eigenvalue.
+  double lo = std::numeric_limits<double>::max(), hi = -lo;
+  for (int j = 0; j < K; ++j) {
+    const double r = (j ? std::abs(e[j - 1]) : 0.0) + (j + 1 < K ? std::abs(e[j]) : 0.0);
+    lo = std::min(lo, d[j] - r);
+    hi = std::max(hi, d[j] + r);
+  }
+  auto count_below = [&](double lam) {
+    int cnt  = 0;
+    double q = d[0] - lam;
+    if (q < 0) ++cnt;
+    for (int j = 1; j < K; ++j) {
+      if (q == 0.0) q = 1e-300;
+      q = d[j] - lam - e[j - 1] * e[j - 1] / q;
+      if (q < 0) ++cnt;
+    }
+    return cnt;
+  };
+  for (int it = 0; it < 300 && hi - lo > 2e-16 * std::max(1.0, std::abs(lo) + std::abs(hi)); ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (count_below(mid) >= 1) hi = mid;
+    else lo = mid;
+  }
+  const double chi   = 0.5 * (lo + hi);
+  const double shift = chi - 1e-9 * std::max(1.0, std::abs(chi));
+  // inverse iteration with an LDL^T factorisation of A - shift I (positive definite)
+  std::vector<double> piv(K), l(K, 0.0), v(K, 1.0);
+  piv[0] = d[0] - shift;
+  for (int j = 1; j < K; ++j) {
+    l[j]   = e[j - 1] / piv[j - 1];
+    piv[j] = d[j] - shift - l[j] * e[j - 1];
+  }
+  for (int j = 0; j < K; ++j)
+    if (!(piv[j] > 0.0) || !std::isfinite(piv[j])) return;  // ok_ stays false
+  for (int it = 0; it < 5; ++it) {
+    for (int j = 1; j < K; ++j) v[j] -= l[j] * v[j - 1];
+    for (int j = 0; j < K; ++j) v[j] /= piv[j];
+    for (int j = K - 2; j >= 0; --j) v[j] -= l[j + 1] * v[j + 1];
+    double nrm = 0;
+    for (double t : v) nrm += t * t;
+    nrm = 1.0 / std::sqrt(nrm);
+    for (double &t : v) t *= nrm;
+  }
+  // to plain Legendre coefficients; drop the negligible tail
+  double big = 0;
+  for (int j = 0; j < K; ++j) {
+    v[j] *= std::sqrt(2.0 * j + 0.5);
+    big = std::max(big, std::abs(v[j]));
+  }
+  int last = 0;
+  for (int j = 0; j < K; ++j)
+    if (std::abs(v[j]) > 1e-18 * big) last = j;
+  leg_.assign(v.begin(), v.begin() + last + 1);
+  const double at0 = series(0.0);
+  if (at0 == 0.0 || !std::isfinite(at0)) return;
+  scale_ = 1.0 / at0;
+  ok_    = true;
+}
+
+double Prolate0::series(double x) const {
+  // sum_j leg_[j] P_{2j}(x) by the three-term recurrence on all degrees
+  double pm = 1.0, p = x, s = leg_[0];
+  const int top = 2 * ((int)leg_.size() - 1);
+  for (int n = 1; n < top; ++n) {
+    const double pn = ((2.0 * n + 1.0) * x * p - n * pm) / (n + 1.0);  // P_{n+1}
+    pm = p;
+    p  = pn;
+    if (((n + 1) & 1) == 0) s += leg_[(n + 1) / 2] * p;
+  }
+  return s;
+}
+
+double Prolate0::operator()(double x) const {
+  if (std::abs(x) > 1.0) return 0.0;
+  return series(x) * scale_;
+}
+
+// ------------------------------------------------------------------ polynomial table
+// Interpolate g on the n first-kind Chebyshev nodes and return monomial coefficients,
+// highest degree first.  Arithmetic in T (the reference fits in the plan's precision).
+template<class T, class G> static std::vector<T> cheb_fit_monomial(G &&g, int n) {
+  std::vector<T> node(n), dd(n);
+  for (int k = 0; k < n; ++k) {
+    node[k] = (T)std::cos(((double)T(2 * k + 1) * kPi) / (double)(T(2) * T(n)));
+    dd[k]   = (T)g(node[k]);
+  }
+  for (int lvl = 1; lvl < n; ++lvl)  // Newton divided differences, in place
+    for (int i = n - 1; i >= lvl; --i) dd[i] = (dd[i] - dd[i - 1]) / (node[i] - node[i - lvl]);
+  std::vector<T> mono(n, T(0)), prod(1, T(1)), next;
+  mono[0] += dd[0];
+  for (int lvl = 1; lvl < n; ++lvl) {  // prod <- prod * (t - node[lvl-1]), low -> high
+    const T root = node[lvl - 1];
+    next.assign(prod.size() + 1, T(0));
+    for (size_t i = 0; i < prod.size(); ++i) {
+      next[i] += -root * prod[i];
+      next[i + 1] += prod[i];
+    }
+    prod.swap(next);
+    for (size_t i = 0; i < prod.size(); ++i) mono[i] += dd[lvl] * prod[i];
+  }
+  std::reverse(mono.begin(), mono.end());
+  return mono;
+}
+
+template<class T>
+int build_horner_table(int ns, double beta, T tol, std::vector<T> &coef, int &nc) {
+  Prolate0 psi(beta);
+  if (!psi.ok()) return ERR_PSWF_SETUP;
+  const int nfit = std::min(kMaxNc, ns + 3);
+  std::vector<T> full((size_t)nfit * ns);
+  int need_max = 4;
+  for (int j = 0; j < ns; ++j) {
+    const T centre = T(2 * j + 1 - ns);  // panel j is [-1+2j/ns, -1+2(j+1)/ns] in window units
+    auto panel = [&](T u) -> T { return (T)psi((double)((u + centre) / (T)ns)); };
+    const std::vector<T> cj = cheb_fit_monomial<T>(panel, nfit);
+    for (int k = 0; k < nfit; ++k) full[(size_t)k * ns + j] = cj[k];
+    const T small = tol * T(0.05);  // leading coefficients below this are dropped
+    for (int k = 0; k < nfit; ++k)
+      if (std::abs(cj[k]) >= small) {
+        need_max = std::max(need_max, nfit - k);
+        break;
+      }
+  }
+  nc = std::max(need_max, std::max(4, ns - 4));
+  coef.assign(full.begin() + (size_t)(nfit - nc) * ns, full.end());
+  return 0;
+}
+template int build_horner_table<float>(int, double, float, std::vector<float> &, int &);
+template int build_horner_table<double>(int, double, double, std::vector<double> &, int &);
+
+template<class T> double eval_table(double x, int ns, int nc, const T *coef) {
+  const double half = 0.5 * ns;
+  if (!(std::abs(x) <= half)) return 0.0;
+  int j = (int)std::ceil(x + half) - 1;  // panel with x in (-half+j, -half+j+1]
+  j     = std::min(std::max(j, 0), ns - 1);
+  const double z = 2.0 * (x - j) + (ns - 1);
+  double r = 0.0;
+  for (int k = 0; k < nc; ++k) r = r * z + (double)coef[(size_t)k * ns + j];
+  return r;
+}
+template double eval_table<float>(double, int, int, const float *);
+template double eval_table<double>(double, int, int, const double *);
+
+// ------------------------------------------------------------------ grid sizes
+static bool is_smooth235(int64_t n) {
+  for (int p : {2, 3, 5})
+    while (n % p == 0) n /= p;
+  return n == 1;
+}
+int64_t next_smooth_even(int64_t n) {
+  int64_t h = std::max<int64_t>((n + 1) / 2, 1);
+  while (!is_smooth235(h)) ++h;
+  return 2 * h;
+}
+int64_t fine_grid_size(double sigma, int64_t modes, int ns) {
+  int64_t nf = (int64_t)std::ceil(sigma * (double)modes);
+  nf         = std::max<int64_t>(nf, 2 * ns);
+  if (nf >= (int64_t)1e12) return -1;
+  return next_smooth_even(nf);
+}
+
+// ------------------------------------------------------------------ quadrature
+void gauss_legendre(int n, double *x, double *w) {
+  // Newton on P_n from Chebyshev guesses; weights 2 / ((1-x^2) P_n'(x)^2).
+  for (int i = 0; i < (n + 1) / 2; ++i) {
+    double t = std::cos(kPi * (i + 0.75) / (n + 0.5));
+    double dp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p0 = 1.0, p1 = t;
+      for (int k = 1; k < n; ++k) {
+        const double p2 = ((2.0 * k + 1.0) * t * p1 - k * p0) / (k + 1.0);
+        p0 = p1;
+        p1 = p2;
+      }
+      dp = n * (t * p1 - p0) / (t * t - 1.0);
+      const double dt = p1 / dp;
+      t -= dt;
+      if (std::abs(dt) < 1e-15) {
+        // refresh derivative at the converged node
+        p0 = 1.0, p1 = t;
+        for (int k = 1; k < n; ++k) {
+          const double p2 = ((2.0 * k + 1.0) * t * p1 - k * p0) / (k + 1.0);
+          p0 = p1;
+          p1 = p2;
+        }
+        dp = n * (t * p1 - p0) / (t * t - 1.0);
+        break;
+      }
+    }
+    const double wt = 2.0 / ((1.0 - t * t) * dp * dp);
+    x[i]         = -t;
+    x[n - 1 - i] = t;
+    w[i] = w[n - 1 - i] = wt;
+  }
+  if (n & 1) x[n / 2] = 0.0;
+}
+
+template<class T> int fseries_nodes(int ns, int nc, const T *coef, double *z, double *f) {
+  const double half = 0.5 * ns;
+  const int q       = (int)(2 + 3.0 * half);  // same node count as the reference
+  std::vector<double> x(2 * q), w(2 * q);
+  gauss_legendre(2 * q, x.data(), w.data());
+  for (int n = 0; n < q; ++n) {  // the q negative nodes; the window is even
+    z[n] = x[n] * half;
+    f[n] = half * w[n] * eval_table<T>(z[n], ns, nc, coef);
+  }
+  return q;
+}
+template int fseries_nodes<float>(int, int, const float *, double *, double *);
+template int fseries_nodes<double>(int, int, const double *, double *, double *);
+
+// ------------------------------------------------------------------ sigma feasibility
+static double sigma_reaching(double tol, int dim, int type, int ns) {
+  const double pre = aliasing_prefactor(dim, type);
+  if (tol <= 0) return 2.5;
+  if (tol >= pre) return 1.01;
+  const double u = std::log(pre / tol) / ((ns - 1.0) * kPi);
+  if (u >= 1.0) return 2.5;
+  return std::min(1.0 / (1.0 - u * u), 2.5);
+}
+double least_sigma(double tol, int dim, int ns, double eps_mach, double gridlen) {
+  // src/common/kernel.cpp:172-201: analytic inversion of the aliasing law, plus an
+  // empirical 1/r polynomial near the rounding floor eps_round = 0.48 eps N.
+  const double r = tol / (0.48 * eps_mach * gridlen);
+  if (r <= 0.5) return 2.0;
+  const double pure = sigma_reaching(tol, dim, 1, ns);
+  if (r >= 10.0) return std::min(pure, 2.0);
+  const bool wide = ns > 8;
+  const double a2 = wide ? 0.014 : 0.555, a1 = wide ? 0.291 : -0.290, a0 = wide ? -0.043 : 0.071;
+  const double corr = (a2 / r + a1) / r + a0;
+  return std::min(pure + std::max(corr, 0.0), 2.0);
+}
+
+// ------------------------------------------------------------------ type 3
+void type3_grid(double sigma, double X, double S, int ns, int64_t &nf, double &h, double &gam) {
+  double Xs = X, Ss = S;  // enforce X*S >= 1, also when either is zero
+  if (Xs == 0.0) {
+    if (Ss == 0.0) Xs = Ss = 1.0;
+    else Xs = 1.0 / Ss;
+  } else {
+    Ss = std::max(Ss, 1.0 / Xs);
+  }
+  double want = 2.0 * sigma * Ss * Xs / kPi + (ns + 1);
+  if (!std::isfinite(want)) want = 0.0;
+  nf = std::max<int64_t>((int64_t)want, 2 * ns);
+  if (nf < (int64_t)1e12) nf = next_smooth_even(nf);
+  h   = 2.0 * kPi / (double)nf;
+  gam = (double)nf / (2.0 * sigma * Ss);
+}
+
+template<class T>
+void selfft_params(int ns, double beta, int nc, const T *coef, double &grid_scale,
+                   double &prefac) {
+  // integral of the tabulated window: per panel, int_{-1}^{1} sum_k c_k z^(nc-1-k) dz / 2;
+  // odd powers vanish, even power p contributes c/(p+1).
+  double total = 0.0;
+  for (int j = 0; j < ns; ++j)
+    for (int k = nc - 1; k >= 0; k -= 2) total += (double)coef[(size_t)k * ns + j] / (nc - k);
+  prefac     = total;
+  grid_scale = 0.25 * ns * ns / beta;
+}
+template void selfft_params<float>(int, double, int, const float *, double &, double &);
+template void selfft_params<double>(int, double, int, const double *, double &, double &);
+
+}  // namespace b200

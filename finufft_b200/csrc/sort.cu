@@ -1,0 +1,344 @@
+// setpts kernels: bin keys, stable LSD radix sort, bin bounds, coordinate gather, subproblems.
+// See sort.cuh for the contract and the reference lines the permutation must reproduce.
+#include "devmath.cuh"
+#include "sort.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------ bin keys
+template<class T, int DIM>
+__global__ void k_bin_keys(const T *__restrict__ x, const T *__restrict__ y,
+                           const T *__restrict__ z, uint32_t M, GridGeom<T> g,
+                           uint32_t *__restrict__ keys) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
+    // 1/binsize are powers of two, so the product is exact; conversion truncates (X >= 0).
+    uint32_t key = (uint32_t)(int)mul_rn(fold_rescale<T>(x[i], g.nf_t[0]), (T)(1.0 / kBinX));
+    if (DIM > 1)
+      key += (uint32_t)g.nb[0] *
+             (uint32_t)(int)mul_rn(fold_rescale<T>(y[i], g.nf_t[1]), (T)(1.0 / kBinY));
+    if (DIM > 2)
+      key += (uint32_t)g.nb[0] * (uint32_t)g.nb[1] *
+             (uint32_t)(int)mul_rn(fold_rescale<T>(z[i], g.nf_t[2]), (T)(1.0 / kBinZ));
+    keys[i] = key < g.nbins ? key : g.nbins - 1;  // only non-finite input can trip this
+  }
+}
+
+static inline int grid_for(uint32_t n, int threads, int per_sm = 8) {
+  const long long want = ((long long)n + threads - 1) / threads;
+  const long long cap  = 148LL * per_sm;
+  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+template<class T>
+void launch_bin_keys(int dim, const T *x, const T *y, const T *z, uint32_t M,
+                     const GridGeom<T> &g, uint32_t *keys, cudaStream_t st) {
+  if (M == 0) return;
+  const int nb = grid_for(M, 256);
+  if (dim == 1) k_bin_keys<T, 1><<<nb, 256, 0, st>>>(x, y, z, M, g, keys);
+  else if (dim == 2) k_bin_keys<T, 2><<<nb, 256, 0, st>>>(x, y, z, M, g, keys);
+  else k_bin_keys<T, 3><<<nb, 256, 0, st>>>(x, y, z, M, g, keys);
+}
+template void launch_bin_keys<float>(int, const float *, const float *, const float *, uint32_t,
+                                     const GridGeom<float> &, uint32_t *, cudaStream_t);
+template void launch_bin_keys<double>(int, const double *, const double *, const double *,
+                                      uint32_t, const GridGeom<double> &, uint32_t *,
+                                      cudaStream_t);
+
+// ------------------------------------------------------------------------------ block scan
+template<int NT>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *warp_sums,
+                                                         uint32_t &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < NT / 32 ? warp_sums[lane] : 0u, wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += up;
+    }
+    if (lane < NT / 32) warp_sums[lane] = wi - w;
+    if (lane == 31) warp_sums[32] = wi;
+  }
+  __syncthreads();
+  total                = warp_sums[32];
+  const uint32_t result = incl - v + warp_sums[warp];
+  __syncthreads();
+  return result;
+}
+
+// ------------------------------------------------------------------------------ device scan
+constexpr int kScanThreads = 512, kScanItems = 8, kScanChunk = kScanThreads * kScanItems;
+
+__global__ void k_scan_partial(const uint32_t *__restrict__ in, uint32_t n,
+                               uint32_t *__restrict__ partial) {
+  __shared__ uint32_t ws[33];
+  const uint32_t base = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (base + k < n) s += in[base + k];
+  uint32_t tot;
+  block_exclusive_scan<kScanThreads>(s, ws, tot);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+__global__ void k_scan_partials_inplace(uint32_t *partial, uint32_t nblk) {
+  __shared__ uint32_t ws[33];
+  uint32_t carry = 0;
+  for (uint32_t c0 = 0; c0 < nblk; c0 += 1024) {
+    const uint32_t i = c0 + threadIdx.x;
+    const uint32_t v = i < nblk ? partial[i] : 0u;
+    uint32_t tot;
+    const uint32_t ex = block_exclusive_scan<1024>(v, ws, tot);
+    if (i < nblk) partial[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) partial[nblk] = carry;
+}
+__global__ void k_scan_final(const uint32_t *__restrict__ in, uint32_t n,
+                             const uint32_t *__restrict__ partial, uint32_t nblk,
+                             uint32_t *__restrict__ out) {
+  __shared__ uint32_t ws[33];
+  const uint32_t base = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  uint32_t v[kScanItems], s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    s += v[k];
+  }
+  uint32_t tot;
+  uint32_t run = block_exclusive_scan<kScanThreads>(s, ws, tot) + partial[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = partial[nblk];
+}
+void exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *tmp,
+                        cudaStream_t st) {
+  const uint32_t nblk = (n + kScanChunk - 1) / kScanChunk;
+  if (nblk == 0) {
+    cudaMemsetAsync(out, 0, sizeof(uint32_t), st);
+    return;
+  }
+  k_scan_partial<<<nblk, kScanThreads, 0, st>>>(in, n, tmp);
+  k_scan_partials_inplace<<<1, 1024, 0, st>>>(tmp, nblk);
+  k_scan_final<<<nblk, kScanThreads, 0, st>>>(in, n, tmp, nblk, out);
+}
+
+// ------------------------------------------------------------------------------ radix sort
+// One pass = histogram per block (digit-major), scan, stable scatter.  Blocks own contiguous
+// ranges of the input, walked tile by tile, so order inside a digit is input order.
+constexpr int kRsThreads = 256, kRsItems = 8, kRsTile = kRsThreads * kRsItems, kRsWarps = 8;
+
+__global__ void k_radix_hist(const uint32_t *__restrict__ keys, uint32_t M, int shift,
+                             uint32_t mask, uint32_t per_block, uint32_t *__restrict__ hist) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t lo = blockIdx.x * per_block;
+  const uint32_t hi = min(M, lo + per_block);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += kRsThreads)
+    atomicAdd(&h[(keys[i] >> shift) & mask], 1u);
+  __syncthreads();
+  if (threadIdx.x <= mask) hist[threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kRsThreads)
+k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t M,
+                int shift, uint32_t mask, uint32_t per_block,
+                const uint32_t *__restrict__ hist_scanned) {
+  __shared__ uint32_t warp_cnt[kRsWarps][256];
+  __shared__ uint32_t run_base[256];
+  __shared__ uint32_t tile_base[256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  if (threadIdx.x <= mask) run_base[threadIdx.x] = hist_scanned[threadIdx.x * gridDim.x + blockIdx.x];
+  const uint32_t lo = blockIdx.x * per_block;
+  const uint32_t hi = min(M, lo + per_block);
+  for (uint32_t t0 = lo; t0 < hi; t0 += kRsTile) {
+#pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) warp_cnt[w][threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t key[kRsItems], val[kRsItems], rank[kRsItems];
+    const uint32_t wbase = t0 + warp * (32 * kRsItems);
+#pragma unroll
+    for (int k = 0; k < kRsItems; ++k) {
+      const uint32_t e  = wbase + k * 32 + lane;
+      const bool valid  = e < hi;
+      key[k]            = valid ? keys_in[e] : 0xffffffffu;
+      val[k]            = valid ? (vals_in ? vals_in[e] : e) : 0u;
+      const uint32_t d  = valid ? ((key[k] >> shift) & mask) : 256u;  // 256 groups the invalid lanes
+      const uint32_t peers  = __match_any_sync(0xffffffffu, d);
+      const int leader      = __ffs(peers) - 1;
+      uint32_t old          = 0;
+      if (valid && lane == leader) old = warp_cnt[warp][d];
+      old     = __shfl_sync(0xffffffffu, old, leader);
+      rank[k] = old + __popc(peers & lt_mask);
+      if (valid && lane == leader) warp_cnt[warp][d] = old + __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x <= mask) {  // per digit: exclusive scan over warps, then advance the run
+      uint32_t s = 0;
+#pragma unroll
+      for (int w = 0; w < kRsWarps; ++w) {
+        const uint32_t c = warp_cnt[w][threadIdx.x];
+        warp_cnt[w][threadIdx.x] = s;
+        s += c;
+      }
+      tile_base[threadIdx.x] = run_base[threadIdx.x];
+      run_base[threadIdx.x] += s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kRsItems; ++k) {
+      const uint32_t e = wbase + k * 32 + lane;
+      if (e < hi) {
+        const uint32_t d   = (key[k] >> shift) & mask;
+        const uint32_t pos = tile_base[d] + warp_cnt[warp][d] + rank[k];
+        keys_out[pos]      = key[k];
+        vals_out[pos]      = val[k];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int radix_sort_pairs(uint32_t *keys_a, uint32_t *keys_b, uint32_t *vals_a, uint32_t *vals_b,
+                     uint32_t M, int nbits, uint32_t *hist, uint32_t *scan_tmp, cudaStream_t st) {
+  if (M == 0) return 0;
+  int which = 0;
+  const int npass = (nbits + 7) / 8;
+  if (npass == 0) {
+    launch_iota(vals_a, M, st);
+    return 0;
+  }
+  const int dbits = (nbits + npass - 1) / npass;  // <= 8
+  // block ranges: multiple of the tile, at most kRadixMaxBlocks blocks
+  uint32_t tiles     = (M + kRsTile - 1) / kRsTile;
+  uint32_t nblk      = tiles < kRadixMaxBlocks ? tiles : kRadixMaxBlocks;
+  uint32_t per_block = ((tiles + nblk - 1) / nblk) * kRsTile;
+  nblk               = (M + per_block - 1) / per_block;
+  for (int p = 0; p < npass; ++p) {
+    const int shift     = p * dbits;
+    const int bits      = (shift + dbits <= nbits) ? dbits : nbits - shift;
+    const uint32_t mask = (1u << bits) - 1u;
+    uint32_t *kin = which ? keys_b : keys_a, *kout = which ? keys_a : keys_b;
+    uint32_t *vin = which ? vals_b : vals_a, *vout = which ? vals_a : vals_b;
+    k_radix_hist<<<nblk, kRsThreads, 0, st>>>(kin, M, shift, mask, per_block, hist);
+    exclusive_scan_u32(hist, hist, (mask + 1) * nblk, scan_tmp, st);
+    k_radix_scatter<<<nblk, kRsThreads, 0, st>>>(kin, p == 0 ? nullptr : vin, kout, vout, M,
+                                                  shift, mask, per_block, hist);
+    which ^= 1;
+  }
+  return which;
+}
+
+// ------------------------------------------------------------------------------ bin bounds
+__global__ void k_bin_bounds(const uint32_t *__restrict__ keys, uint32_t M, uint32_t nbins,
+                             uint32_t *__restrict__ binstart) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
+    const uint32_t k = keys[i];
+    if (i == 0) {
+      for (uint32_t b = 0; b <= k; ++b) binstart[b] = 0;
+    } else {
+      const uint32_t prev = keys[i - 1];
+      for (uint32_t b = prev + 1; b <= k; ++b) binstart[b] = i;
+    }
+    if (i == M - 1)
+      for (uint32_t b = k + 1; b <= nbins; ++b) binstart[b] = M;
+  }
+}
+void launch_bin_bounds(const uint32_t *sorted_keys, uint32_t M, uint32_t nbins,
+                       uint32_t *binstart, cudaStream_t st) {
+  if (M == 0) {
+    cudaMemsetAsync(binstart, 0, sizeof(uint32_t) * ((size_t)nbins + 1), st);
+    return;
+  }
+  k_bin_bounds<<<grid_for(M, 256), 256, 0, st>>>(sorted_keys, M, nbins, binstart);
+}
+
+// ------------------------------------------------------------------------------ gather
+template<class T, int DIM>
+__global__ void k_gather_coords(const T *__restrict__ x, const T *__restrict__ y,
+                                const T *__restrict__ z, const uint32_t *__restrict__ sidx,
+                                uint32_t M, T *__restrict__ xs, T *__restrict__ ys,
+                                T *__restrict__ zs) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
+    const uint32_t j = sidx[i];
+    xs[i] = x[j];
+    if (DIM > 1) ys[i] = y[j];
+    if (DIM > 2) zs[i] = z[j];
+  }
+}
+template<class T>
+void launch_gather_coords(int dim, const T *x, const T *y, const T *z, const uint32_t *sidx,
+                          uint32_t M, T *xs, T *ys, T *zs, cudaStream_t st) {
+  if (M == 0) return;
+  const int nb = grid_for(M, 256, 16);
+  if (dim == 1) k_gather_coords<T, 1><<<nb, 256, 0, st>>>(x, y, z, sidx, M, xs, ys, zs);
+  else if (dim == 2) k_gather_coords<T, 2><<<nb, 256, 0, st>>>(x, y, z, sidx, M, xs, ys, zs);
+  else k_gather_coords<T, 3><<<nb, 256, 0, st>>>(x, y, z, sidx, M, xs, ys, zs);
+}
+template void launch_gather_coords<float>(int, const float *, const float *, const float *,
+                                          const uint32_t *, uint32_t, float *, float *, float *,
+                                          cudaStream_t);
+template void launch_gather_coords<double>(int, const double *, const double *, const double *,
+                                           const uint32_t *, uint32_t, double *, double *,
+                                           double *, cudaStream_t);
+
+// ------------------------------------------------------------------------------ subproblems
+__global__ void k_sub_count(const uint32_t *__restrict__ binstart, uint32_t nbins,
+                            uint32_t maxsub, uint32_t *__restrict__ nsub) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nbins; b += stride) {
+    const uint32_t n = binstart[b + 1] - binstart[b];
+    nsub[b]          = (n + maxsub - 1) / maxsub;
+  }
+}
+__global__ void k_sub_fill(const uint32_t *__restrict__ binstart,
+                           const uint32_t *__restrict__ substart, uint32_t nbins,
+                           uint32_t maxsub, uint32_t *__restrict__ sub_bin,
+                           uint32_t *__restrict__ sub_off) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nbins; b += stride) {
+    const uint32_t s0 = substart[b], s1 = substart[b + 1];
+    uint32_t off = binstart[b];
+    for (uint32_t s = s0; s < s1; ++s, off += maxsub) {
+      sub_bin[s] = b;
+      sub_off[s] = off;
+    }
+  }
+}
+void launch_sub_count(const uint32_t *binstart, uint32_t nbins, uint32_t maxsub, uint32_t *nsub,
+                      cudaStream_t st) {
+  k_sub_count<<<grid_for(nbins, 256), 256, 0, st>>>(binstart, nbins, maxsub, nsub);
+}
+void launch_sub_fill(const uint32_t *binstart, const uint32_t *substart, uint32_t nbins,
+                     uint32_t maxsub, uint32_t *sub_bin, uint32_t *sub_off, cudaStream_t st) {
+  k_sub_fill<<<grid_for(nbins, 256), 256, 0, st>>>(binstart, substart, nbins, maxsub, sub_bin,
+                                                   sub_off);
+}
+
+__global__ void k_iota(uint32_t *v, uint32_t n) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = i;
+}
+void launch_iota(uint32_t *v, uint32_t n, cudaStream_t st) {
+  if (n) k_iota<<<grid_for(n, 256), 256, 0, st>>>(v, n);
+}
+
+}  // namespace b200

@@ -1,0 +1,58 @@
+// setpts on the device: bin keys, stable LSD radix sort of (bin key, point index), bin
+// boundaries, gather of coordinates into sorted order, subproblem list.
+//
+// The permutation produced is bit-identical to the reference CPU library's stable counting
+// sort over 16x4x4-cell bins (include/finufft/spread.hpp:459-584 with the bin sizes of
+// include/finufft/spreadinterp.hpp:159): bin = i1 + nb1*(i2 + nb2*i3),
+// i_d = trunc(fold_rescale(x_d, N_d) * (1/binsize_d)), nb_d = trunc(T(N_d)/binsize_d + 1),
+// ties in ascending original index.  A stable radix sort of ascending indices by that key
+// is exactly that order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kBinX = 16, kBinY = 4, kBinZ = 4;
+
+template<class T> struct GridGeom {
+  int nf[3];      // fine grid size per dim (1 for unused dims)
+  T nf_t[3];      // the same, converted to T the way the CPU code does (T(N))
+  int nb[3];      // bins per dim
+  uint32_t nbins; // total bins
+};
+
+// --- launchers (defined in sort.cu) -------------------------------------------------------
+template<class T>
+void launch_bin_keys(int dim, const T *x, const T *y, const T *z, uint32_t M,
+                     const GridGeom<T> &g, uint32_t *keys, cudaStream_t st);
+
+// Stable sort of keys (only the low `nbits` bits are significant) carrying values; on entry
+// values are implicit 0..M-1.  Uses keys_a/keys_b and vals_a/vals_b as ping-pong buffers and
+// `hist` (>= 256*kRadixMaxBlocks+1 words).  Returns which buffer (0 = a, 1 = b) holds the
+// result.
+constexpr uint32_t kRadixMaxBlocks = 148 * 8;
+int radix_sort_pairs(uint32_t *keys_a, uint32_t *keys_b, uint32_t *vals_a, uint32_t *vals_b,
+                     uint32_t M, int nbits, uint32_t *hist, uint32_t *scan_tmp, cudaStream_t st);
+
+// binstart[b] = first sorted position whose key >= b, b = 0..nbins (binstart[nbins] = M).
+void launch_bin_bounds(const uint32_t *sorted_keys, uint32_t M, uint32_t nbins,
+                       uint32_t *binstart, cudaStream_t st);
+
+template<class T>
+void launch_gather_coords(int dim, const T *x, const T *y, const T *z, const uint32_t *sidx,
+                          uint32_t M, T *xs, T *ys, T *zs, cudaStream_t st);
+
+// Exclusive scan of n words; out[n] receives the total (out has n+1 entries). tmp >= n/4096+2.
+void exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *tmp,
+                        cudaStream_t st);
+
+// nsub[b] = ceil(count_b / maxsub);  then (after a scan) the per-subproblem (bin, start) list.
+void launch_sub_count(const uint32_t *binstart, uint32_t nbins, uint32_t maxsub, uint32_t *nsub,
+                      cudaStream_t st);
+void launch_sub_fill(const uint32_t *binstart, const uint32_t *substart, uint32_t nbins,
+                     uint32_t maxsub, uint32_t *sub_bin, uint32_t *sub_off, cudaStream_t st);
+
+void launch_iota(uint32_t *v, uint32_t n, cudaStream_t st);
+
+}  // namespace b200

@@ -1,0 +1,6 @@
+// Instantiates the spread / interp kernels for float, 1D, every supported kernel width.
+#include "spreadinterp.cuh"
+#define B200_NS_LIST B200_NS_CASE(2) B200_NS_CASE(3) B200_NS_CASE(4) B200_NS_CASE(5) B200_NS_CASE(6) B200_NS_CASE(7) B200_NS_CASE(8) B200_NS_CASE(9) B200_NS_CASE(10) B200_NS_CASE(11) B200_NS_CASE(12)
+namespace b200 {
+B200_DEFINE_LAUNCH(float, 1)
+}
