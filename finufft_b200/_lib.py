@@ -81,7 +81,9 @@ SIMPLE_GPU = [f"cufinufft{p}{d}d{t}{m}" for p in ("", "f") for d in (1, 2, 3)
 SIMPLE_HOST = [f"finufft{p}{d}d{t}{m}" for p in ("", "f") for d in (1, 2, 3)
                for t in (1, 2, 3) for m in ("", "many")]
 INTROSPECT = ["b200_get_plan_info", "b200_get_sort_permutation", "b200_get_window_table",
-              "b200_get_phihat", "b200_version"]
+              "b200_get_phihat", "b200_enable_profiling", "b200_get_stage_ms",
+              "b200_get_launch_count", "b200_host_kernel", "b200_host_fine_grid",
+              "b200_host_fseries", "b200_version"]
 ALL_SYMBOLS = GURU_GPU + GURU_HOST + SIMPLE_GPU + SIMPLE_HOST + INTROSPECT
 
 _lib = None
@@ -137,6 +139,19 @@ def load():
     lib.b200_get_window_table.restype = ci
     lib.b200_get_phihat.argtypes = [vp, ci, vp]
     lib.b200_get_phihat.restype = ci
+    lib.b200_enable_profiling.argtypes = [vp, ci]
+    lib.b200_enable_profiling.restype = ci
+    lib.b200_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 5)]
+    lib.b200_get_stage_ms.restype = ci
+    lib.b200_get_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.b200_get_launch_count.restype = ci
+    lib.b200_host_kernel.argtypes = [dbl, ci, ci, dbl, ci, ci, C.POINTER(ci), C.POINTER(dbl),
+                                     C.POINTER(ci), vp]
+    lib.b200_host_kernel.restype = ci
+    lib.b200_host_fine_grid.argtypes = [dbl, i64, ci]
+    lib.b200_host_fine_grid.restype = i64
+    lib.b200_host_fseries.argtypes = [i64, ci, ci, ci, vp, vp]
+    lib.b200_host_fseries.restype = ci
     lib.b200_version.restype = C.c_char_p
     _lib = lib
     return lib

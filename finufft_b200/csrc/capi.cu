@@ -5,6 +5,7 @@
 // of reference include/finufft_common/safe_call.h:57-80.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <limits>
@@ -14,6 +15,7 @@
 #include "../../include/b200_finufft.h"
 #include "../../include/b200_introspect.h"
 #include "engine.hpp"
+#include "planmath.hpp"
 
 using namespace b200;
 
@@ -603,6 +605,64 @@ int b200_get_phihat(void *plan, int d, void *host_out) {
     } else {
       DeviceGuard g(as_plan<double>(plan)->eng.opts.device);
       as_plan<double>(plan)->eng.copy_phihat_to_host(d, (double *)host_out);
+    }
+  });
+}
+int b200_enable_profiling(void *plan, int on) {
+  return guarded([&] {
+    auto *b = static_cast<PlanBase *>(plan);
+    if (!b || b->magic != kMagic) throw Failure{ERR_PLAN_NOTVALID};
+    if (b->is_float) as_plan<float>(plan)->eng.enable_profiling(on != 0);
+    else as_plan<double>(plan)->eng.enable_profiling(on != 0);
+  });
+}
+int b200_get_stage_ms(void *plan, float ms[5]) {
+  return guarded([&] {
+    auto *b = static_cast<PlanBase *>(plan);
+    if (!b || b->magic != kMagic || !ms) throw Failure{ERR_PLAN_NOTVALID};
+    if (b->is_float) as_plan<float>(plan)->eng.stage_ms(ms);
+    else as_plan<double>(plan)->eng.stage_ms(ms);
+  });
+}
+int b200_get_launch_count(void *plan, uint64_t *count) {
+  return guarded([&] {
+    auto *b = static_cast<PlanBase *>(plan);
+    if (!b || b->magic != kMagic || !count) throw Failure{ERR_PLAN_NOTVALID};
+    *count = b->is_float ? as_plan<float>(plan)->eng.launches : as_plan<double>(plan)->eng.launches;
+  });
+}
+int b200_host_kernel(double tol, int dim, int type, double sigma, int is_float, int allow_small,
+                     int *ns, double *beta, int *nc, void *coef) {
+  return guarded([&] {
+    double tol_used;
+    int err = choose_kernel(tol, dim, type, sigma, is_float != 0, allow_small != 0, *ns, *beta,
+                            tol_used);
+    if (err) throw Failure{err};
+    if (is_float) {
+      std::vector<float> c;
+      err = build_horner_table<float>(*ns, *beta, (float)tol_used, c, *nc);
+      if (err) throw Failure{err};
+      std::memcpy(coef, c.data(), c.size() * sizeof(float));
+    } else {
+      std::vector<double> c;
+      err = build_horner_table<double>(*ns, *beta, tol_used, c, *nc);
+      if (err) throw Failure{err};
+      std::memcpy(coef, c.data(), c.size() * sizeof(double));
+    }
+  });
+}
+int64_t b200_host_fine_grid(double sigma, int64_t modes, int ns) {
+  return fine_grid_size(sigma, modes, ns);
+}
+int b200_host_fseries(int64_t nf, int ns, int nc, int is_float, const void *coef, double *out) {
+  return guarded([&] {
+    double z[kMaxQuad], f[kMaxQuad];
+    const int q = is_float ? fseries_nodes<float>(ns, nc, (const float *)coef, z, f)
+                           : fseries_nodes<double>(ns, nc, (const double *)coef, z, f);
+    for (int64_t k = 0; k <= nf / 2; ++k) {
+      double s = 0;
+      for (int n = 0; n < q; ++n) s += 2.0 * f[n] * std::cos(2.0 * kPi * ((double)k * (z[n] / (double)nf)));
+      out[k] = (k & 1) ? -s : s;
     }
   });
 }

@@ -84,6 +84,38 @@ Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr
 
 template<class T> Engine<T>::~Engine() {
   if (have_fft_) cufftDestroy(fft_);
+  for (auto &e : ev_)
+    if (e) cudaEventDestroy(e);
+}
+
+template<class T> void Engine<T>::enable_profiling(bool on) {
+  DeviceGuard guard(opts.device);
+  prof_ = on;
+  if (on)
+    for (auto &e : ev_)
+      if (!e) CU(cudaEventCreate(&e));
+}
+template<class T> void Engine<T>::mark(int i) {
+  if (prof_) cudaEventRecord(ev_[i], opts.stream);
+}
+template<class T> void Engine<T>::stage_ms(float out[5]) {
+  for (int i = 0; i < 5; ++i) out[i] = 0.f;
+  if (!prof_) return;
+  DeviceGuard guard(opts.device);
+  cudaStreamSynchronize(opts.stream);
+  // order_ maps {spread/interp, fft, deconv} to the event intervals of the last execute
+  float a = 0, b = 0, c = 0;
+  if (cudaEventElapsedTime(&a, ev_[0], ev_[1]) != cudaSuccess) a = 0;
+  if (cudaEventElapsedTime(&b, ev_[1], ev_[2]) != cudaSuccess) b = 0;
+  if (cudaEventElapsedTime(&c, ev_[2], ev_[3]) != cudaSuccess) c = 0;
+  const float iv[3] = {a, b, c};
+  out[0] = iv[order_[0]];
+  out[1] = iv[order_[1]];
+  out[2] = iv[order_[2]];
+  out[3] = a + b + c;
+  float sp = 0;
+  if (cudaEventElapsedTime(&sp, ev_[4], ev_[5]) == cudaSuccess) out[4] = sp;
+  cudaGetLastError();
 }
 
 template<class T> void Engine<T>::plan_kernel() {
@@ -218,7 +250,9 @@ void Engine<T>::setpts(int64_t M_, const T *x, const T *y, const T *z, int64_t N
   }
   for (int d = 0; d < dim; ++d)
     if (nf[d] < 2 * ns) throw Failure{ERR_SPREAD_BOX_SMALL};
+  mark(4);
   sort_points(x, y, z);
+  mark(5);
 }
 
 // ------------------------------------------------------------------ execute
@@ -235,6 +269,7 @@ template<class T> void Engine<T>::run_spread(const C *c, C *fw) {
     e = launch_spreadinterp<T, 3>(true, ns, pts, geom, nc, coef.data(), c, nullptr, fw, opts.stream);
   if (e == cudaErrorInvalidConfiguration) throw Failure{ERR_INSUFFICIENT_SHMEM};
   CU(e);
+  ++launches;
 }
 template<class T> void Engine<T>::run_interp(C *c, const C *fw) {
   if (nsub == 0) return;
@@ -250,6 +285,7 @@ template<class T> void Engine<T>::run_interp(C *c, const C *fw) {
     e = launch_spreadinterp<T, 3>(false, ns, pts, geom, nc, coef.data(), nullptr, c, fwm, opts.stream);
   if (e == cudaErrorInvalidConfiguration) throw Failure{ERR_INSUFFICIENT_SHMEM};
   CU(e);
+  ++launches;
 }
 
 // NU strengths -> modes: spread, FFT, deconvolve (include/finufft/execute.hpp:376-417, type 1)
@@ -266,11 +302,21 @@ template<class T> void Engine<T>::spread_path(C *c, C *fk, int fsign) {
   for (int b0 = 0; b0 < ntr; b0 += batch) {
     const int nb = std::min(batch, ntr - b0);
     C *grid      = opts.spreadinterponly ? fk + (int64_t)b0 * Nm : fw_.p;
+    order_[0] = 0, order_[1] = 1, order_[2] = 2;
+    mark(0);
     CU(cudaMemsetAsync(grid, 0, sizeof(C) * (size_t)G * nb, st));
     for (int i = 0; i < nb; ++i) run_spread(c + (int64_t)(b0 + i) * M, grid + (int64_t)i * G);
-    if (opts.spreadinterponly) continue;
+    mark(1);
+    if (opts.spreadinterponly) {
+      mark(2);
+      mark(3);
+      continue;
+    }
     fft_exec(fft_, fw_.p, fsign);
+    mark(2);
     launch_grid_to_modes<T>(dim, nb, fw_.p, fk + (int64_t)b0 * Nm, mg, st);
+    ++launches;
+    mark(3);
   }
   CU(cudaGetLastError());
 }
@@ -289,12 +335,21 @@ template<class T> void Engine<T>::interp_path(C *c, C *fk, int fsign) {
   for (int b0 = 0; b0 < ntr; b0 += batch) {
     const int nb  = std::min(batch, ntr - b0);
     const C *grid = fw_.p;
-    if (opts.spreadinterponly) grid = fk + (int64_t)b0 * Nm;
-    else {
+    order_[0] = 2, order_[1] = 1, order_[2] = 0;  // intervals: amplify, fft, interp
+    mark(0);
+    if (opts.spreadinterponly) {
+      grid = fk + (int64_t)b0 * Nm;
+      mark(1);
+      mark(2);
+    } else {
       launch_modes_to_grid<T>(dim, nb, fk + (int64_t)b0 * Nm, fw_.p, mg, st);
+      ++launches;
+      mark(1);
       fft_exec(fft_, fw_.p, fsign);
+      mark(2);
     }
     for (int i = 0; i < nb; ++i) run_interp(c + (int64_t)(b0 + i) * M, grid + (int64_t)i * G);
+    mark(3);
   }
   CU(cudaGetLastError());
 }

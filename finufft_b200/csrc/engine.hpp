@@ -81,6 +81,12 @@ template<class T> class Engine {
   void copy_sort_to_host(uint32_t *out) const;
   void copy_phihat_to_host(int d, T *out) const;
   cudaStream_t stream() const { return opts.stream; }
+  // stage timing (CUDA events on the plan's stream) and launch accounting for benches
+  void enable_profiling(bool on);
+  // ms of the last execute: [0] spread or interp, [1] FFT, [2] deconvolve/amplify, [3] total;
+  // ms of the last setpts in [4]
+  void stage_ms(float out[5]);
+  uint64_t launches = 0;  // kernels of this library launched so far (cuFFT/memset excluded)
 
  private:
   void plan_kernel();
@@ -94,6 +100,10 @@ template<class T> class Engine {
   void setpts_type3(int64_t M, const T *x, const T *y, const T *z, int64_t N, const T *s,
                     const T *t, const T *u);
 
+  bool prof_ = false;
+  cudaEvent_t ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int order_[4] = {0, 1, 2, 3};
+  void mark(int i);
   DevBuf<T> phihat_[3];
   DevBuf<C> fw_;
   cufftHandle fft_ = 0;

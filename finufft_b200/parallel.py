@@ -1,0 +1,76 @@
+"""Multi-GPU sharding of the hot path across one 8xB200 box (one process per GPU).
+
+The path shards where the reference's own batching does: the `ntransf` strength vectors of a
+vectorised transform are independent given the points (include/finufft/execute.hpp:376-382:
+cjb = cj + b*nj, fkb = fk + b*N).  Each rank keeps a full copy of the points (setpts is
+replicated; 20 B/point once) and executes its contiguous slice of the vectors on its own GPU
+with no data-path collective.  Only if the caller wants every rank to hold the full result is
+one all_gather issued at the end (NCCL over NVLink on GPUs, gloo in the CPU tests).
+
+The single-large-transform case (z-slab decomposition of the fine grid with ghost-plane
+exchange and a distributed FFT) is the next row; it is not built yet.
+"""
+from typing import Callable, List, Tuple
+
+
+def split_transforms(ntr: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous [start, stop) slice of the ntr vectors for every rank; sizes differ by at
+    most one, earlier ranks get the larger share, empty slices allowed when world > ntr."""
+    if ntr < 0 or world < 1:
+        raise ValueError("ntr >= 0 and world >= 1 required")
+    base, extra = divmod(ntr, world)
+    out, start = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((start, start + n))
+        start += n
+    return out
+
+
+class BatchSplit:
+    """Runs a vectorised transform with its vectors split across the ranks of a process group.
+
+    make_plan(n_local) -> object with setpts(*pts) and execute(data) (a finufft_b200.Plan on
+    this rank's GPU).  data_in is the FULL (ntr, ...) input, present on every rank (or only the
+    local slice if `local_only`).
+    """
+
+    def __init__(self, ntr: int, make_plan: Callable, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.ntr = ntr
+        self.slices = split_transforms(ntr, self.world)
+        self.lo, self.hi = self.slices[self.rank]
+        self.plan = make_plan(self.hi - self.lo) if self.hi > self.lo else None
+
+    def setpts(self, *pts):
+        if self.plan is not None:
+            self.plan.setpts(*pts)
+
+    def execute_local(self, data_full):
+        """This rank's slice of the outputs (None if the slice is empty)."""
+        if self.plan is None:
+            return None
+        local = data_full[self.lo:self.hi]
+        if self.hi - self.lo == 1:
+            return self.plan.execute(local[0]).unsqueeze(0)
+        return self.plan.execute(local.contiguous())
+
+    def execute_gathered(self, data_full, out_shape_per_vector):
+        """Full (ntr, ...) result on every rank: local execute + one all_gather."""
+        import torch
+        mine = self.execute_local(data_full)
+        if self.world == 1:
+            return mine
+        nmax = max(hi - lo for lo, hi in self.slices)
+        ref = mine if mine is not None else data_full
+        buf = torch.zeros((nmax,) + tuple(out_shape_per_vector), dtype=data_full.dtype,
+                          device=ref.device)
+        if mine is not None:
+            buf[: mine.shape[0]] = mine
+        parts = [torch.empty_like(buf) for _ in range(self.world)]
+        self.dist.all_gather(parts, buf, group=self.group)
+        return torch.cat([p[: hi - lo] for p, (lo, hi) in zip(parts, self.slices)], dim=0)

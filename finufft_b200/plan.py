@@ -69,6 +69,20 @@ class _PlanCommon:
                "get_table")
         return out
 
+    def enable_profiling(self, on=True):
+        _check(self._lib.b200_enable_profiling(self._plan, int(on)), "enable_profiling")
+
+    def stage_ms(self):
+        """dict of ms for the last execute / setpts (CUDA events on the plan's stream)."""
+        ms = (C.c_float * 5)()
+        _check(self._lib.b200_get_stage_ms(self._plan, C.byref(ms)), "stage_ms")
+        return dict(spreadinterp=ms[0], fft=ms[1], deconv=ms[2], execute=ms[3], setpts=ms[4])
+
+    def launch_count(self):
+        n = C.c_uint64()
+        _check(self._lib.b200_get_launch_count(self._plan, C.byref(n)), "launch_count")
+        return int(n.value)
+
     def phihat(self, d):
         """Fourier series of the window for LIBRARY dimension d (0 = x = fastest)."""
         nf = self.info()["nf"][d]

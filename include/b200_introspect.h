@@ -24,6 +24,22 @@ int b200_get_sort_permutation(void *plan, uint32_t *host_out);
 int b200_get_window_table(void *plan, void *host_out);
 /* window Fourier series of dimension d, nf[d]/2+1 entries of the plan's real type */
 int b200_get_phihat(void *plan, int d, void *host_out);
+/* stage timing: CUDA events on the plan's stream around the stages of execute and setpts.
+ * ms[0] spread|interp, ms[1] FFT (cuFFT), ms[2] deconvolve|amplify, ms[3] their sum, all for
+ * the LAST execute (last batch); ms[4] the last setpts. */
+int b200_enable_profiling(void *plan, int on);
+int b200_get_stage_ms(void *plan, float ms[5]);
+/* number of this library's own kernels launched by the plan so far (cuFFT, memset excluded) */
+int b200_get_launch_count(void *plan, uint64_t *count);
+/* Host-only plan mathematics (no GPU needed): what makeplan would decide.
+ * b200_host_kernel: width ns, shape beta, polynomial table (nc*ns values of float or double
+ * written to coef, which must hold 19*16 entries), returns 0 or a FINUFFT_ERR_* code.
+ * b200_host_fine_grid: fine-grid length for `modes` modes (or -1 if above 1e12).
+ * b200_host_fseries: window Fourier series k=0..nf/2 in double from a table. */
+int b200_host_kernel(double tol, int dim, int type, double sigma, int is_float, int allow_small,
+                     int *ns, double *beta, int *nc, void *coef);
+int64_t b200_host_fine_grid(double sigma, int64_t modes, int ns);
+int b200_host_fseries(int64_t nf, int ns, int nc, int is_float, const void *coef, double *out);
 /* library build tag, e.g. "finufft_b200 0.1 sm_100a" */
 const char *b200_version(void);
 

@@ -1,0 +1,62 @@
+"""CPU-only: the product's own host-side plan mathematics (finufft_b200/csrc/planmath.cpp,
+reached through the b200_host_* entry points) against the oracle."""
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def hm():
+    from finufft_b200 import hostmath
+    return hostmath
+
+
+CASES = [(1e-6, 3, 1, 2.0, np.float32), (1e-5, 2, 2, 2.0, np.float32), (1e-9, 2, 1, 2.0, np.float64),
+         (1e-9, 1, 1, 2.0, np.float64), (1e-6, 3, 3, 1.25, np.float32), (1e-3, 2, 1, 2.0, np.float32),
+         (1e-12, 3, 1, 2.0, np.float64), (1e-2, 1, 2, 1.25, np.float64), (1e-14, 1, 1, 2.0, np.float64)]
+
+
+@pytest.mark.parametrize("tol,dim,typ,sigma,dt", CASES)
+def test_kernel_choice_and_table(hm, oracle, tol, dim, typ, sigma, dt):
+    err, ns, beta, tab = hm.kernel(tol, dim, typ, sigma, dt)
+    oerr, ons, obeta, otol = oracle.kernel_setup(tol, dim, typ, sigma, dt, True)
+    assert err == oerr == 0 and ns == ons and abs(beta - obeta) < 1e-13
+    ocoef, onc = oracle.horner(ons, obeta, otol, dt)
+    assert tab.shape == (onc, ons)
+    # same kernel FUNCTION: compare evaluated window values over the support (coefficients of
+    # high-degree fits are ill-conditioned, the values are not)
+    xs = np.linspace(-ns / 2 + 1e-3, -ns / 2 + 1 - 1e-3, 23)
+    ours = np.array([oracle.eval_stencil(dt(x), tab) for x in xs], dtype=np.float64)
+    ref = np.array([oracle.eval_stencil(dt(x), ocoef) for x in xs], dtype=np.float64)
+    eps = np.finfo(dt).eps
+    assert np.max(np.abs(ours - ref)) <= 64 * eps
+    if dt == np.float32 and ns <= 10:
+        assert np.array_equal(tab, ocoef)
+
+
+def test_error_codes(hm):
+    assert hm.kernel(1e-6, 3, 1, 1.0, np.float32)[0] == 7
+    assert hm.kernel(1e-9, 3, 1, 2.0, np.float32, allow_small=False)[0] == 26
+    assert hm.kernel(1e-9, 3, 1, 2.0, np.float32, allow_small=True)[0] == 0
+    assert hm.kernel(1e-20, 1, 1, 2.0, np.float64, allow_small=False)[0] == 26
+
+
+def test_fine_grid_sizes(hm, oracle):
+    for sigma in (2.0, 1.25):
+        for ns in (2, 7, 16):
+            for modes in list(range(1, 200)) + [256, 2048, 1000000, 12345]:
+                want = oracle.next235(max(int(np.ceil(sigma * modes)), 2 * ns), 2)
+                assert hm.fine_grid(sigma, modes, ns) == want
+    assert hm.fine_grid(2.0, 256, 7) == 512 and hm.fine_grid(2.0, 2048, 6) == 4096
+    assert hm.fine_grid(2.0, 10 ** 12, 7) == -1
+
+
+@pytest.mark.parametrize("dt,tol", [(np.float32, 1e-6), (np.float64, 1e-9)])
+def test_fseries_matches_oracle(hm, oracle, dt, tol):
+    err, ns, beta, tab = hm.kernel(tol, 1, 1, 2.0, dt)
+    for nf in (2 * ns, 90, 512):
+        ours = hm.fseries(nf, tab)
+        ref = oracle.fseries(nf, tab).astype(np.float64)
+        # the oracle follows the reference's working-precision phase winding; ours is double
+        bound = 2e-5 if dt == np.float32 else 1e-12
+        assert np.max(np.abs(ours - ref)) <= bound * abs(ref[0])
+        assert ours[0] > 0 and np.all(np.sign(ours[: nf // 4]) == (-1.0) ** np.arange(nf // 4))
