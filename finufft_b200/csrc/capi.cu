@@ -654,15 +654,16 @@ int b200_host_kernel(double tol, int dim, int type, double sigma, int is_float, 
 int64_t b200_host_fine_grid(double sigma, int64_t modes, int ns) {
   return fine_grid_size(sigma, modes, ns);
 }
-int b200_host_fseries(int64_t nf, int ns, int nc, int is_float, const void *coef, double *out) {
+int b200_host_fseries(int64_t nf, int ns, int nc, int is_float, const void *coef, void *out) {
   return guarded([&] {
-    double z[kMaxQuad], f[kMaxQuad];
-    const int q = is_float ? fseries_nodes<float>(ns, nc, (const float *)coef, z, f)
-                           : fseries_nodes<double>(ns, nc, (const double *)coef, z, f);
-    for (int64_t k = 0; k <= nf / 2; ++k) {
-      double s = 0;
-      for (int n = 0; n < q; ++n) s += 2.0 * f[n] * std::cos(2.0 * kPi * ((double)k * (z[n] / (double)nf)));
-      out[k] = (k & 1) ? -s : s;
+    if (is_float) {
+      std::vector<float> ph;
+      fseries_wound<float>(nf, ns, nc, (const float *)coef, ph);
+      std::memcpy(out, ph.data(), ph.size() * sizeof(float));
+    } else {
+      std::vector<double> ph;
+      fseries_wound<double>(nf, ns, nc, (const double *)coef, ph);
+      std::memcpy(out, ph.data(), ph.size() * sizeof(double));
     }
   });
 }

@@ -161,13 +161,21 @@ template<class T> void Engine<T>::plan_grid() {
   if (opts.spreadinterponly) return;
 
   cudaStream_t st = opts.stream;
-  for (int d = 0; d < dim; ++d) {
+  for (int d = 0; d < dim; ++d) {  // plan-time, O(nf * ns): host, in the reference's arithmetic
     phihat_[d].alloc(nf[d] / 2 + 1);
-    FseriesNodes nodes;
-    nodes.q = fseries_nodes<T>(ns, nc, coef.data(), nodes.z, nodes.f);
-    launch_fseries<T>(nf[d], nodes, phihat_[d].p, st);
+    int same = -1;
+    for (int e = 0; e < d; ++e)
+      if (nf[e] == nf[d]) same = e;
+    if (same >= 0) {
+      CU(cudaMemcpyAsync(phihat_[d].p, phihat_[same].p, sizeof(T) * (nf[d] / 2 + 1),
+                         cudaMemcpyDeviceToDevice, st));
+      continue;
+    }
+    std::vector<T> ph;
+    fseries_wound<T>(nf[d], ns, nc, coef.data(), ph);
+    CU(cudaMemcpyAsync(phihat_[d].p, ph.data(), sizeof(T) * ph.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // ph is a temporary
   }
-  CU(cudaGetLastError());
   fw_.alloc((size_t)total * batch);
   if (have_fft_) {
     cufftDestroy(fft_);

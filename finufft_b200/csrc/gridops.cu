@@ -1,6 +1,5 @@
 // Uniform-grid side of the transform: deconvolve + mode-order copy (type 1), amplify +
-// zero-pad (type 2), the window's Fourier series on the fine grid, and the element-wise
-// multiplies type 3 needs.
+// zero-pad (type 2), and the element-wise multiplies type 3 needs.
 //
 // Spec: include/finufft/execute.hpp:69-237 (deconvolveshuffle1d/2d/3d): per dimension
 // kmin = -(ms/2), kmax = (ms-1)/2; k >= 0 lives at fine index k, k < 0 at nf+k; modeord 0
@@ -111,26 +110,6 @@ void launch_modes_to_grid(int dim, int batch, const typename CxOf<T>::type *fk,
   else k_modes_to_grid<T, 3><<<grid, 256, 0, st>>>(fk, fw, g);
 }
 
-// phihat[k] = sum_n 2 f_n cos(k theta_n + k pi), theta_n = 2 pi z_n / nf, k = 0..nf/2.
-// Phase taken in turns (k z_n / nf) in double so large k loses no accuracy.
-template<class T>
-__global__ void k_fseries(int64_t nf, FseriesNodes nodes, T *__restrict__ out) {
-  const int64_t nout   = nf / 2 + 1;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nout; k += stride) {
-    double s = 0.0;
-    for (int n = 0; n < nodes.q; ++n) {
-      const double turns = (double)k * (nodes.z[n] / (double)nf);
-      s += 2.0 * nodes.f[n] * cospi(2.0 * turns);
-    }
-    out[k] = (T)((k & 1) ? -s : s);
-  }
-}
-template<class T>
-void launch_fseries(int64_t nf, const FseriesNodes &nodes, T *out, cudaStream_t st) {
-  k_fseries<T><<<blocks_for(nf / 2 + 1, 128), 128, 0, st>>>(nf, nodes, out);
-}
-
 // ---- type 3 element-wise helpers -----------------------------------------------------------
 template<class T>
 __global__ void k_cmul(const typename CxOf<T>::type *__restrict__ a,
@@ -161,7 +140,6 @@ void launch_cmul(int batch, const typename CxOf<T>::type *a, const typename CxOf
                                         const ModeGeom<T> &, cudaStream_t);                    \
   template void launch_modes_to_grid<T>(int, int, const CxOf<T>::type *, CxOf<T>::type *,      \
                                         const ModeGeom<T> &, cudaStream_t);                    \
-  template void launch_fseries<T>(int64_t, const FseriesNodes &, T *, cudaStream_t);           \
   template void launch_cmul<T>(int, const CxOf<T>::type *, const CxOf<T>::type *,              \
                                CxOf<T>::type *, int64_t, int, cudaStream_t);
 B200_INST(float)

@@ -14,20 +14,12 @@ template<class T> struct ModeGeom {
   const T *ph[3];   // window Fourier series, indices 0..nf/2, device pointers
 };
 
-struct FseriesNodes {
-  int q;
-  double z[100];
-  double f[100];
-};
-
 template<class T>
 void launch_grid_to_modes(int dim, int batch, const typename CxOf<T>::type *fw,
                           typename CxOf<T>::type *fk, const ModeGeom<T> &g, cudaStream_t st);
 template<class T>
 void launch_modes_to_grid(int dim, int batch, const typename CxOf<T>::type *fk,
                           typename CxOf<T>::type *fw, const ModeGeom<T> &g, cudaStream_t st);
-template<class T>
-void launch_fseries(int64_t nf, const FseriesNodes &nodes, T *out, cudaStream_t st);
 template<class T>
 void launch_cmul(int batch, const typename CxOf<T>::type *a, const typename CxOf<T>::type *b,
                  typename CxOf<T>::type *out, int64_t n, int conj_b, cudaStream_t st);

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <limits>
 
 #include "errors.hpp"
@@ -255,19 +256,45 @@ void gauss_legendre(int n, double *x, double *w) {
   if (n & 1) x[n / 2] = 0.0;
 }
 
-template<class T> int fseries_nodes(int ns, int nc, const T *coef, double *z, double *f) {
-  const double half = 0.5 * ns;
-  const int q       = (int)(2 + 3.0 * half);  // same node count as the reference
+// window value at grid-unit argument x, all arithmetic in T with fused Horner steps
+template<class T> static T eval_table_native(T x, int ns, int nc, const T *coef) {
+  const T half = ns / T(2.0);
+  for (int j = 0; j < ns; ++j)
+    if (x > -half + j && x <= -half + j + 1) {
+      const T z = std::fma(T(2.0), x - T(j), T(ns - 1));
+      T r       = T(0);
+      for (int k = 0; k < nc; ++k) r = std::fma(r, z, coef[(size_t)k * ns + j]);
+      return r;
+    }
+  return T(0);
+}
+
+template<class T>
+void fseries_wound(int64_t nf, int ns, int nc, const T *coef, std::vector<T> &out) {
+  const T half = ns / 2.0;
+  const int q  = (int)(2 + 3.0 * half);
   std::vector<double> x(2 * q), w(2 * q);
   gauss_legendre(2 * q, x.data(), w.data());
-  for (int n = 0; n < q; ++n) {  // the q negative nodes; the window is even
-    z[n] = x[n] * half;
-    f[n] = half * w[n] * eval_table<T>(z[n], ns, nc, coef);
+  std::vector<T> f(q);
+  std::vector<std::complex<T>> rot(q), cur(q, std::complex<T>(1, 0));
+  for (int n = 0; n < q; ++n) {
+    const double zn = x[n] * half;  // node in (-ns/2, 0)
+    f[n]            = half * (T)w[n] * eval_table_native<T>(T(zn), ns, nc, coef);
+    const std::complex<double> a = -std::exp(2 * kPi * std::complex<double>(0, 1) * zn / double(nf));
+    rot[n] = std::complex<T>((T)a.real(), (T)a.imag());
   }
-  return q;
+  out.resize(nf / 2 + 1);
+  for (int64_t k = 0; k <= nf / 2; ++k) {
+    T s = 0.0;
+    for (int n = 0; n < q; ++n) {
+      s += f[n] * 2 * std::real(cur[n]);
+      cur[n] *= rot[n];
+    }
+    out[k] = s;
+  }
 }
-template int fseries_nodes<float>(int, int, const float *, double *, double *);
-template int fseries_nodes<double>(int, int, const double *, double *, double *);
+template void fseries_wound<float>(int64_t, int, int, const float *, std::vector<float> &);
+template void fseries_wound<double>(int64_t, int, int, const double *, std::vector<double> &);
 
 // ------------------------------------------------------------------ sigma feasibility
 static double sigma_reaching(double tol, int dim, int type, int ns) {

@@ -57,11 +57,13 @@ int64_t fine_grid_size(double sigma, int64_t modes, int ns);
 // n-point Gauss-Legendre rule on [-1,1], nodes ascending.
 void gauss_legendre(int n, double *x, double *w);
 
-// Quadrature data for the window's Fourier series: q nodes z_n in (-ns/2,0) and weights
-// f_n = (ns/2) w_n phi(z_n), so that phihat(k) = sum_n 2 f_n cos(k*theta_n + k*pi),
-// theta_n = 2 pi z_n / nf.  phi is the polynomial table evaluated in double.
+// Window Fourier series phihat[k], k = 0..nf/2, computed the way the reference CPU library
+// does (include/finufft/makeplan.hpp:72-105, single chunk): node weights and the phase
+// rotators a_n = -exp(2 pi i z_n / nf) are held in the plan's precision T and wound by repeated
+// complex multiplication, phihat[k] = sum_n 2 f_n Re(a_n^k).  In single precision this drifts
+// by ~k*eps; it is reproduced deliberately so the deconvolution factors equal the reference's.
 template<class T>
-int fseries_nodes(int ns, int nc, const T *coef, double *z, double *f);
+void fseries_wound(int64_t nf, int ns, int nc, const T *coef, std::vector<T> &out);
 
 // Evaluate the table at grid-unit argument x in [-ns/2, ns/2] (double arithmetic).
 template<class T> double eval_table(double x, int ns, int nc, const T *coef);

@@ -27,8 +27,8 @@ def fine_grid(sigma, modes, ns):
 
 def fseries(nf, table):
     nc, ns = table.shape
-    out = np.zeros(nf // 2 + 1)
     t = np.ascontiguousarray(table)
+    out = np.zeros(nf // 2 + 1, dtype=t.dtype)
     err = _lib.load().b200_host_fseries(nf, ns, nc, int(t.dtype == np.float32),
                                         t.ctypes.data_as(C.c_void_p),
                                         out.ctypes.data_as(C.c_void_p))

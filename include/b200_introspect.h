@@ -35,11 +35,11 @@ int b200_get_launch_count(void *plan, uint64_t *count);
  * b200_host_kernel: width ns, shape beta, polynomial table (nc*ns values of float or double
  * written to coef, which must hold 19*16 entries), returns 0 or a FINUFFT_ERR_* code.
  * b200_host_fine_grid: fine-grid length for `modes` modes (or -1 if above 1e12).
- * b200_host_fseries: window Fourier series k=0..nf/2 in double from a table. */
+ * b200_host_fseries: window Fourier series k=0..nf/2 from a table, in the table's precision. */
 int b200_host_kernel(double tol, int dim, int type, double sigma, int is_float, int allow_small,
                      int *ns, double *beta, int *nc, void *coef);
 int64_t b200_host_fine_grid(double sigma, int64_t modes, int ns);
-int b200_host_fseries(int64_t nf, int ns, int nc, int is_float, const void *coef, double *out);
+int b200_host_fseries(int64_t nf, int ns, int nc, int is_float, const void *coef, void *out);
 /* library build tag, e.g. "finufft_b200 0.1 sm_100a" */
 const char *b200_version(void);
 

@@ -81,7 +81,7 @@ def test_plan_parameters_match_oracle(cuda, oracle):
             assert np.array_equal(gcoef, ocoef)
         for d in range(len(modes)):
             ph = gp.phihat(d)
-            assert np.max(np.abs(ph - oph[d])) <= (3e-6 if prec == "f" else 1e-12) * abs(oph[d][0])
+            assert np.max(np.abs(ph - oph[d])) <= 4 * np.finfo(ph.dtype).eps * abs(oph[d][0])
         gp.destroy()
 
 
@@ -352,4 +352,7 @@ def test_full_size_properties(cuda, oracle, workload):
         exact = np.sum(hc * np.exp(1j * ph))
         got = hfk[tuple(kk + m // 2 for kk, m in zip(k, modes))]
         worst = max(worst, abs(got - exact) / scale)
-    assert worst <= 10 * tol
+    # single precision cannot beat the rounding floor eps_round = 0.48*eps*max(nf) of the fine
+    # grid (reference include/finufft/setpts.hpp:29-53; it is why the CPU library needs
+    # allow_eps_too_small for this config): 2.9e-5 at nf=512, 2.3e-4 at nf=4096
+    assert worst <= max(10 * tol, 0.48 * np.finfo(np.float32).eps * max(nf))
