@@ -4,10 +4,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <limits>
 
 #include "planmath.hpp"
 #include "spreadinterp.cuh"
+#include "sweep3d.cuh"
 
 namespace b200 {
 
@@ -75,6 +77,7 @@ Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr
   sigma = opts.upsampfac == 0.0 ? 2.0 : opts.upsampfac;
   batch = opts.maxbatch > 0 ? std::min(opts.maxbatch, ntr) : std::min(ntr, 8);
   if (opts.maxsub < 32) opts.maxsub = 32;
+  if (const char *env = getenv("B200_NUFFT_SWEEP")) opts.sweep = atoi(env);  // debugging aid
   plan_kernel();
   if (type != 3) {
     for (int d = 0; d < dim; ++d) ms[d] = nmodes[d];
@@ -264,12 +267,32 @@ void Engine<T>::setpts(int64_t M_, const T *x, const T *y, const T *z, int64_t N
 }
 
 // ------------------------------------------------------------------ execute
+// The tube-sweep kernels (sweep3d.cuh) take 3D single-precision grids whose x rows can be
+// addressed in aligned 16-byte pairs.
+template<class T> bool Engine<T>::use_sweep3(const void *grid) const {
+  return std::is_same<T, float>::value && dim == 3 && sweep3_supported(ns) && opts.sweep &&
+         nf[0] % 2 == 0 && (reinterpret_cast<uintptr_t>(grid) & 15) == 0;
+}
+static cudaError_t sweep_spread_impl(int ns, const PointSet<float> &pts, const GridGeom<float> &g,
+                                     int nc, const float *coef, const float2 *c, float2 *fw,
+                                     cudaStream_t st) {
+  return launch_spread3_sweep(ns, pts, g, nc, coef, c, fw, st);
+}
+static cudaError_t sweep_spread_impl(int, const PointSet<double> &, const GridGeom<double> &, int,
+                                     const double *, const double2 *, double2 *, cudaStream_t) {
+  return cudaErrorInvalidValue;
+}
+template<class T> cudaError_t Engine<T>::sweep_spread(const PointSet<T> &pts, const C *c, C *fw) {
+  return sweep_spread_impl(ns, pts, geom, nc, coef.data(), c, fw, opts.stream);
+}
 template<class T> void Engine<T>::run_spread(const C *c, C *fw) {
   if (nsub == 0) return;
   PointSet<T> pts{xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, sub_bin_.p, sub_off_.p, nsub,
                   (uint32_t)opts.maxsub};
   cudaError_t e;
-  if (dim == 1)
+  if (use_sweep3(fw))
+    e = sweep_spread(pts, c, fw);
+  else if (dim == 1)
     e = launch_spreadinterp<T, 1>(true, ns, pts, geom, nc, coef.data(), c, nullptr, fw, opts.stream);
   else if (dim == 2)
     e = launch_spreadinterp<T, 2>(true, ns, pts, geom, nc, coef.data(), c, nullptr, fw, opts.stream);

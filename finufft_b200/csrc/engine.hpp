@@ -20,6 +20,7 @@
 #include "errors.hpp"
 #include "gridops.cuh"
 #include "sort.cuh"
+#include "spreadinterp.cuh"
 
 namespace b200 {
 
@@ -33,6 +34,7 @@ struct EngineOpts {
   int maxsub           = 1024;  // most points one warp takes from one bin
   int debug            = 0;
   int allow_eps_too_small = 1;
+  int sweep            = 1;     // 3D float: tube-sweep kernels (0 = generic kernels)
   int check_sigma      = 0;     // host (finufft_*) entry points apply the CPU feasibility rule
 };
 
@@ -92,6 +94,8 @@ template<class T> class Engine {
   void plan_kernel();
   void plan_grid();
   void sort_points(const T *x, const T *y, const T *z);
+  bool use_sweep3(const void *grid) const;
+  cudaError_t sweep_spread(const PointSet<T> &pts, const C *c, C *fw);
   void run_spread(const C *c, C *fw);
   void run_interp(C *c, const C *fw);
   void spread_path(C *c, C *fk, int fsign);
