@@ -2,6 +2,7 @@
 #include "sweep3d.cuh"
 
 #include <limits.h>
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -31,37 +32,56 @@ template<int NS> struct SweepCfg {
   static constexpr int PAD   = HL & 1;                 // tile x origin 16*i1-HL-PAD is even
   static constexpr int PITCH = (ROW + PAD + 1) & ~1;   // cells of one tile row (even)
   static constexpr int SP    = 26;                     // staging row pitch in cells (bank spread)
-  static constexpr int ZR    = NS + 1;                 // z rows one z cell's stencils can touch
-  static constexpr int RZ    = 2;                      // z rows per lane
-  static constexpr int BQ    = (ZR + RZ - 1) / RZ;     // lane groups along z
-  static constexpr int ZS    = RZ * BQ;                // z rows staged per warp (>= ZR)
-  static constexpr int ZT    = kBinZ + NS;             // z rows of the block tile
-  static constexpr int NW    = kBinZ;                  // warps per block = z cells per bin
-  static constexpr int NT    = NW * 32;
-  static constexpr int NSLOT = kBinY;                  // rows leaving the window per step
-  static constexpr int NBUCK = NW * (kBinY + 1);       // (z cell, y stencil start) buckets
-  static constexpr int CH    = 256;                    // points per chunk
-  static constexpr int PPT   = CH / NT;
-  static constexpr int RECW  = 28;                     // words per point record
-  // record: [0,NS) phi_x  [7] x offset  [8,8+NS) phi_y  [16,16+ZS) phi_z window  [24,25] c
-  static constexpr size_t STAGE_BYTES = (size_t)NW * NSLOT * ZS * SP * sizeof(float2);
+  static constexpr int ZT    = kBinZ + NS;             // z rows of the tube tile
+  static constexpr int BQ    = 4;                      // lane groups along z
+  static constexpr int RZ    = (ZT + BQ - 1) / BQ;     // z rows per lane: z = bq + BQ*m
+  static constexpr int ZS    = RZ * BQ;                // z row slots (>= ZT)
+  static constexpr int NJB   = kBinY + 1;              // y stencil starts inside one bin
+  static constexpr int CH    = 64;                     // points per chunk (records in flight)
+  static constexpr int LCAP  = 512;                    // points per sorted batch of one bin
+  static constexpr int RECW  = 36;                     // words per point record
+  // record: [0,NS) phi_x  [7] x offset | jb<<8  [8,8+NS) phi_y  [16+4*bq+m] phi_z of row slot
+  //         (bq,m)  [32,33] strength
+  static constexpr size_t STAGE_BYTES = (size_t)ZS * SP * sizeof(float2);
   static constexpr size_t REC_BYTES   = (size_t)CH * RECW * sizeof(float);
-  static constexpr size_t ORD_BYTES   = (size_t)CH * sizeof(uint16_t);
-  static constexpr size_t BYTES       = STAGE_BYTES + REC_BYTES + ORD_BYTES;
+  static constexpr size_t LIST_BYTES  = (size_t)LCAP * sizeof(uint16_t);
+  static constexpr size_t BYTES       = STAGE_BYTES + REC_BYTES + LIST_BYTES + 64;
   static_assert(PITCH <= SP, "staging pitch");
   static_assert(NS * BQ <= 32, "lane map");
-  static_assert(NS <= 7 && ZS <= 8, "record layout");
+  static_assert(NS <= 7 && RZ <= 3, "record layout");
 };
+
+// Horner table padded to 8 columns so that two neighbouring panels form one aligned pair:
+// c[k*8 + j], k = 0 highest degree, columns j >= NS are zero.
+template<int NS> struct alignas(16) PairTable {
+  float c[TableRows<NS>::value * 8];
+};
+// NS window values by packed Horner (two panels per FFMA2); same roundings as eval_window.
+template<int NS>
+__device__ __forceinline__ void eval_window2(const PairTable<NS> &tab, float x1, float (&out)[8]) {
+  const float z = fma_rn(2.0f, x1, (float)(NS - 1));
+  float2 r[4];
+#pragma unroll
+  for (int p = 0; p < (NS + 1) / 2; ++p) {
+    r[p] = *reinterpret_cast<const float2 *>(&tab.c[2 * p]);
+#pragma unroll
+    for (int k = 1; k < TableRows<NS>::value; ++k)
+      r[p] = ffma2_s(z, r[p], *reinterpret_cast<const float2 *>(&tab.c[k * 8 + 2 * p]));
+    out[2 * p]     = r[p].x;
+    out[2 * p + 1] = r[p].y;
+  }
+}
 
 template<int NS> struct SweepArgs {
   PointSet<float> pts;
   GridGeom<float> g;
-  WindowTable<float, NS> tab;
+  PairTable<NS> tab;
   const float2 *c_in;
   float2 *c_out;
   float2 *fw;
   int nsplit;  // y ranges per tube
   int ypi;     // y bins per item
+  int dbg;     // experiment switches (0 in production)
 };
 
 __device__ __forceinline__ int pmod(int v, int n) {
@@ -89,62 +109,75 @@ __device__ __forceinline__ void row_update_switch(
     B200_XO(8) B200_XO(9) B200_XO(10) B200_XO(11) B200_XO(12) B200_XO(13) B200_XO(14)
     B200_XO(15) B200_XO(16)
 #undef B200_XO
-  default: break;
+  default: __builtin_unreachable();
   }
 }
 
-// Phase A for one point: fold, stencil starts, windows, strength -> record; returns its bucket.
-template<int NS>
-__device__ __forceinline__ int make_record(const SweepArgs<NS> &a, uint32_t q, float *rec, int i1,
-                                           int i2, int i3, bool spread) {
+// y stencil start of a point relative to the first one possible in y bin i2, in [0, kBinY]
+template<int NS> __device__ __forceinline__ int y_bucket(float y, float nf2_t, int i2) {
+  int j0;
+  float y1;
+  stencil_start<float, NS>(fold_rescale<float>(y, nf2_t), j0, y1);
+  return min(max(j0 - (kBinY * i2 - SweepCfg<NS>::HL), 0), kBinY);
+}
+
+// Thread-per-point preparation: fold, stencil starts, windows, strength -> record.
+template<int NS, bool SPREAD>
+__device__ __forceinline__ void make_record(const SweepArgs<NS> &a, uint32_t q, float *rec, int i1,
+                                            int i2, int i3) {
   using CF = SweepCfg<NS>;
+  float2 c = make_float2(0.f, 0.f);
+  if (SPREAD) c = __ldcs(a.c_in + __ldcs(a.pts.sidx + q));
   int i0;
   float x1;
-  stencil_start<float, NS>(fold_rescale<float>(a.pts.xs[q], a.g.nf_t[0]), i0, x1);
-  eval_window<float, NS>(a.tab, x1, rec);
-  int xo = i0 - (kBinX * i1 - CF::HL);
-  xo     = min(max(xo, 0), kBinX);
-  rec[7] = __int_as_float(xo);
-  stencil_start<float, NS>(fold_rescale<float>(a.pts.ys[q], a.g.nf_t[1]), i0, x1);
-  eval_window<float, NS>(a.tab, x1, rec + 8);
-  int jb = i0 - (kBinY * i2 - CF::HL);
-  jb     = min(max(jb, 0), kBinY);
-  const float Z = fold_rescale<float>(a.pts.zs[q], a.g.nf_t[2]);
-  stencil_start<float, NS>(Z, i0, x1);
-  float kz[NS];
-  eval_window<float, NS>(a.tab, x1, kz);
-  int wz = (int)floorf(Z) - kBinZ * i3;
-  wz     = min(max(wz, 0), kBinZ - 1);
-  int zsh = i0 - (kBinZ * i3 + wz - CF::HL);  // 0 or 1 (clamped: the rows must stay in the window)
-  zsh     = min(max(zsh, 0), CF::ZS - NS);
+  float kv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  stencil_start<float, NS>(fold_rescale<float>(__ldcs(a.pts.ys + q), a.g.nf_t[1]), i0, x1);
+  eval_window2<NS>(a.tab, x1, kv);
+  *reinterpret_cast<float4 *>(rec + 8)  = make_float4(kv[0], kv[1], kv[2], kv[3]);
+  *reinterpret_cast<float4 *>(rec + 12) = make_float4(kv[4], kv[5], kv[6], 0.f);
+  const int jb = min(max(i0 - (kBinY * i2 - CF::HL), 0), kBinY);
+  stencil_start<float, NS>(fold_rescale<float>(__ldcs(a.pts.xs + q), a.g.nf_t[0]), i0, x1);
+  eval_window2<NS>(a.tab, x1, kv);
+  const int xo = min(max(i0 - (kBinX * i1 - CF::HL), 0), kBinX);
+  kv[7]        = __int_as_float(xo | (jb << 8));
+  *reinterpret_cast<float4 *>(rec)     = make_float4(kv[0], kv[1], kv[2], kv[3]);
+  *reinterpret_cast<float4 *>(rec + 4) = make_float4(kv[4], kv[5], kv[6], kv[7]);
+  stencil_start<float, NS>(fold_rescale<float>(__ldcs(a.pts.zs + q), a.g.nf_t[2]), i0, x1);
+  eval_window2<NS>(a.tab, x1, kv);
+  // z stencil start relative to the tile's first z row, in [0, kBinZ]
+  const int k0 = min(max(i0 - (kBinZ * i3 - CF::HL), 0), kBinZ);
+  // window value of tile row z = bq + BQ*m goes to word 16 + 4*bq + m
 #pragma unroll
-  for (int r = 0; r < CF::ZS; ++r) {
-    float v = 0.f;
+  for (int bq = 0; bq < CF::BQ; ++bq) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int s = 0; s <= CF::ZS - NS; ++s)
-      if (r - s >= 0 && r - s < NS) v = (zsh == s) ? kz[r - s] : v;
-    rec[16 + r] = v;
+    for (int m = 0; m < CF::RZ; ++m) {
+      const int z = bq + CF::BQ * m;
+#pragma unroll
+      for (int s = 0; s <= kBinZ; ++s)
+        if (z - s >= 0 && z - s < NS) v[m] = (k0 == s) ? kv[z - s] : v[m];
+    }
+    *reinterpret_cast<float4 *>(rec + 16 + 4 * bq) = make_float4(v[0], v[1], v[2], v[3]);
   }
-  if (spread) {
-    const float2 c = a.c_in[a.pts.sidx[q]];
-    rec[24]        = c.x;
-    rec[25]        = c.y;
-  }
-  return wz * (kBinY + 1) + jb;
+  *reinterpret_cast<float2 *>(rec + 32) = c;
 }
 
+__device__ __forceinline__ void sts64(uint32_t addr, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// One warp per work item: a tube (x bin i1, z bin i3) over the y bins [yb0, yb1).
 template<int NS>
-__global__ void __launch_bounds__(SweepCfg<NS>::NT, 4) k_spread3_sweep(const SweepArgs<NS> a) {
+__global__ void __launch_bounds__(32, 12) k_spread3_sweep(const SweepArgs<NS> a) {
   using CF = SweepCfg<NS>;
   extern __shared__ __align__(16) unsigned char smem[];
-  float2 *stage   = reinterpret_cast<float2 *>(smem);
-  float *rec      = reinterpret_cast<float *>(smem + CF::STAGE_BYTES);
-  uint16_t *order = reinterpret_cast<uint16_t *>(smem + CF::STAGE_BYTES + CF::REC_BYTES);
-  __shared__ int s_cnt[32], s_base[32];
+  float2 *stage  = reinterpret_cast<float2 *>(smem);
+  float *rec     = reinterpret_cast<float *>(smem + CF::STAGE_BYTES);
+  uint16_t *list = reinterpret_cast<uint16_t *>(smem + CF::STAGE_BYTES + CF::REC_BYTES);
+  int *cnt       = reinterpret_cast<int *>(smem + CF::STAGE_BYTES + CF::REC_BYTES + CF::LIST_BYTES);
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x;
   const int la = lane / CF::BQ, bq = lane % CF::BQ;  // la >= NS: spare lane
-  const bool live = la < NS;
   const int nb1 = a.g.nb[0], nb2 = a.g.nb[1];
   const int tube = blockIdx.x / a.nsplit, part = blockIdx.x % a.nsplit;
   const int i1 = tube % nb1, i3 = tube / nb1;
@@ -154,7 +187,7 @@ __global__ void __launch_bounds__(SweepCfg<NS>::NT, 4) k_spread3_sweep(const Swe
   const int z0t = kBinZ * i3 - CF::HL;
 
   // staging starts zeroed: the pad cells of every row are never written afterwards
-  for (int i = tid; i < (int)(CF::STAGE_BYTES / sizeof(float2)); i += CF::NT)
+  for (int i = lane; i < (int)(CF::STAGE_BYTES / sizeof(float2)); i += 32)
     stage[i] = float2{0.f, 0.f};
 
   float2 acc[CF::RZ][CF::ROW];
@@ -162,130 +195,114 @@ __global__ void __launch_bounds__(SweepCfg<NS>::NT, 4) k_spread3_sweep(const Swe
   for (int r = 0; r < CF::RZ; ++r)
 #pragma unroll
     for (int c = 0; c < CF::ROW; ++c) acc[r][c] = float2{0.f, 0.f};
-  int jw = INT_MIN;  // first y row of the register window (block-uniform); INT_MIN = none
+  int jw = INT_MIN;  // first y row of the register window; INT_MIN = window empty
 
-  float2 *my_stage = stage + ((size_t)(warp * CF::NSLOT) * CF::ZS + bq * CF::RZ) * CF::SP + CF::PAD;
+  const uint32_t my_stage =
+      (uint32_t)__cvta_generic_to_shared(stage + (size_t)bq * CF::SP + CF::PAD);
+  __syncwarp();
 
-  // park this lane's rows in staging slot `slot` and clear them
-  auto stage_rows = [&](int slot) {
-    float2 *dst = my_stage + (size_t)slot * CF::ZS * CF::SP;
+  // The window's first row leaves: its owners park it in the staging tile, then the whole warp
+  // adds the tile row to the fine grid with 16-byte vector reductions.
+  auto slide = [&]() {
+    if (la == pmod(jw, NS)) {
 #pragma unroll
-    for (int r = 0; r < CF::RZ; ++r)
+      for (int m = 0; m < CF::RZ; ++m)
 #pragma unroll
-      for (int c = 0; c < CF::ROW; ++c) {
-        dst[r * CF::SP + c] = acc[r][c];
-        acc[r][c]           = float2{0.f, 0.f};
-      }
-  };
-  // sum the warps' staged rows [yfirst, yfirst+cnt) and add them to the fine grid
-  auto merge = [&](int yfirst, int cnt) {
-    constexpr int NXP = CF::PITCH / 2;
-    for (int idx = tid; idx < cnt * CF::ZT * NXP; idx += CF::NT) {
-      const int xp = idx % NXP, z = (idx / NXP) % CF::ZT, s = idx / (NXP * CF::ZT);
-      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int w = 0; w < CF::NW; ++w) {
-        const int zr = z - w;
-        if (zr >= 0 && zr < CF::ZR) {
-          const float4 v = *reinterpret_cast<const float4 *>(
-              stage + ((size_t)(w * CF::NSLOT + s) * CF::ZS + zr) * CF::SP + 2 * xp);
-          sum.x += v.x, sum.y += v.y, sum.z += v.z, sum.w += v.w;
+        for (int c = 0; c < CF::ROW; ++c) {
+          sts64(my_stage + (uint32_t)((m * CF::BQ * CF::SP + c) * sizeof(float2)), acc[m][c]);
+          acc[m][c] = float2{0.f, 0.f};
         }
-      }
-      if (sum.x != 0.f || sum.y != 0.f || sum.z != 0.f || sum.w != 0.f) {
-        const int gx = wrap_index(x0t + 2 * xp, nf1), gy = wrap_index(yfirst + s, nf2),
-                  gz = wrap_index(z0t + z, nf3);
-        atomicAdd(reinterpret_cast<float4 *>(a.fw + ((size_t)gz * nf2 + gy) * (size_t)nf1 + gx),
-                  sum);
+    }
+    __syncwarp();
+    constexpr int NXP = CF::PITCH / 2;
+    const int gy      = wrap_index(jw, nf2);
+    for (int idx = lane; idx < CF::ZT * NXP; idx += 32) {
+      const int z = idx / NXP, xp = idx - z * NXP;
+      const float4 v = *reinterpret_cast<const float4 *>(stage + (size_t)z * CF::SP + 2 * xp);
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+        const int gx = wrap_index(x0t + 2 * xp, nf1), gz = wrap_index(z0t + z, nf3);
+        if (!(a.dbg & 1))
+          atomicAdd(reinterpret_cast<float4 *>(a.fw + ((size_t)gz * nf2 + gy) * (size_t)nf1 + gx), v);
       }
     }
+    __syncwarp();
+    ++jw;
   };
-  // write out every live row of the window (start of an irregular step, end of the item)
-  auto flush_all = [&]() {
-    if (jw == INT_MIN) return;
-    const int rel = live ? pmod(la - jw, NS) : -1;
-    for (int r0 = 0; r0 < NS; r0 += CF::NSLOT) {
-      const int cnt = min(CF::NSLOT, NS - r0);
-      if (rel >= r0 && rel < r0 + cnt) stage_rows(rel - r0);
-      __syncthreads();
-      merge(jw + r0, cnt);
-      __syncthreads();
+  // move the window so that it starts at row j0 (never backwards unless it is emptied first)
+  auto advance_to = [&](int j0) {
+    if (jw == INT_MIN) {
+      jw = j0;
+      return;
     }
-    jw = INT_MIN;
+    if (j0 < jw || j0 - jw >= NS) {  // rewind or long jump: empty the window
+      for (int k = 0; k < NS; ++k) slide();
+      jw = j0;
+      return;
+    }
+    while (jw < j0) slide();
   };
 
-  __syncthreads();
   for (int i2 = yb0; i2 < yb1; ++i2) {
     const uint32_t bin = (uint32_t)i1 + (uint32_t)nb1 * ((uint32_t)i2 + (uint32_t)nb2 * (uint32_t)i3);
     const uint32_t qs = a.pts.binstart[bin], qe = a.pts.binstart[bin + 1];
-    if (qs == qe && jw == INT_MIN) continue;  // nothing in flight, nothing to do
     const int target = kBinY * i2 - CF::HL;
-    uint32_t qa = qs;
-    do {
-      const uint32_t qb = min(qe, qa + CF::CH);
-      // ---------------- phase A: records + buckets
-      if (tid < 32) s_cnt[tid] = 0;
-      __syncthreads();
-      int mybucket[CF::PPT], mypos[CF::PPT];
-#pragma unroll
-      for (int k = 0; k < CF::PPT; ++k) {
-        const uint32_t slot = tid + k * CF::NT, q = qa + slot;
-        mybucket[k]         = -1;
-        if (q < qb) {
-          mybucket[k] = make_record<NS>(a, q, rec + slot * CF::RECW, i1, i2, i3, true);
-          mypos[k]    = atomicAdd(&s_cnt[mybucket[k]], 1);
+    for (uint32_t q0 = qs; q0 < qe; q0 += CF::LCAP) {
+      const int n = (int)min((uint32_t)CF::LCAP, qe - q0);
+      // ---- sort this batch of the bin by y stencil start (counting sort, 5 buckets)
+      if (lane < 8) cnt[lane] = 0;
+      __syncwarp();
+      for (int k = lane; k < n; k += 32)
+        atomicAdd(&cnt[y_bucket<NS>(a.pts.ys[q0 + k], a.g.nf_t[1], i2)], 1);
+      __syncwarp();
+      if (lane == 0) {
+        int run = 0;
+        for (int b = 0; b < CF::NJB; ++b) {
+          const int c = cnt[b];
+          cnt[b]      = run;
+          run += c;
         }
       }
-      __syncthreads();
-      if (tid < 32) {
-        const int v = s_cnt[tid];
-        int incl    = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int up = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += up;
-        }
-        s_base[tid] = incl - v;
+      __syncwarp();
+      for (int k = lane; k < n; k += 32) {
+        const int pos = atomicAdd(&cnt[y_bucket<NS>(a.pts.ys[q0 + k], a.g.nf_t[1], i2)], 1);
+        list[pos]     = (uint16_t)k;
       }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < CF::PPT; ++k)
-        if (mybucket[k] >= 0) order[s_base[mybucket[k]] + mypos[k]] = (uint16_t)(tid + k * CF::NT);
-      // ---------------- window to the start of this bin (irregular only)
-      if (jw != target) {
-        flush_all();  // contains the barriers
-        jw = target;
-      }
-      __syncthreads();
-      // ---------------- phase B: my z cell's points, in y-stencil-start order
-      for (int jb = 0; jb <= kBinY; ++jb) {
-        const int j0 = target + jb;
-        if (jb > 0 && la == pmod(j0 - 1, NS)) stage_rows(jb - 1);  // row j0-1 leaves the window
-        const int ta  = live ? pmod(la - j0, NS) : 0;
-        const int b   = warp * (kBinY + 1) + jb;
-        const int pb  = s_base[b], pe = pb + s_cnt[b];
-        for (int p = pb; p < pe; ++p) {
-          const float *rp = rec + (int)order[p] * CF::RECW;
+      __syncwarp();
+      for (int c0 = 0; c0 < n; c0 += CF::CH) {
+        const int nc = min(CF::CH, n - c0);
+        // ---- records for the next nc points in sorted order
+        for (int k = lane; k < nc; k += 32)
+          make_record<NS, true>(a, q0 + list[c0 + k], rec + k * CF::RECW, i1, i2, i3);
+        __syncwarp();
+        // ---- accumulate
+        int cur_jb = -1, ta = 0;
+        for (int p = 0; p < ((a.dbg & 2) ? 0 : nc); ++p) {
+          const float *rp = rec + p * CF::RECW;
           const float4 k0 = *reinterpret_cast<const float4 *>(rp);
           const float4 k1 = *reinterpret_cast<const float4 *>(rp + 4);
-          const float2 c  = *reinterpret_cast<const float2 *>(rp + 24);
+          const int meta  = __float_as_int(k1.w);
+          const int jb    = meta >> 8;
+          if (jb != cur_jb) {  // warp-uniform
+            cur_jb = jb;
+            advance_to(target + jb);
+            ta = la < NS ? pmod(la - (target + jb), NS) : 0;
+          }
           const float wy  = rp[8 + ta];
-          const float2 fz = *reinterpret_cast<const float2 *>(rp + 16 + bq * CF::RZ);
+          const float4 fz = *reinterpret_cast<const float4 *>(rp + 16 + 4 * bq);
+          const float2 cw = fmul2_s(wy, *reinterpret_cast<const float2 *>(rp + 32));
           const float kx[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, 0.f};
           float2 w[CF::RZ];
-          w[0] = fmul2_s(wy * fz.x, c);
-          w[1] = fmul2_s(wy * fz.y, c);
-          row_update_switch<NS>(__float_as_int(k1.w), acc, kx, w);
+          w[0] = fmul2_s(fz.x, cw);
+          w[1] = fmul2_s(fz.y, cw);
+          if (CF::RZ > 2) w[CF::RZ - 1] = fmul2_s(fz.z, cw);
+          row_update_switch<NS>(meta & 0xff, acc, kx, w);
         }
+        __syncwarp();
       }
-      jw = target + kBinY;
-      __syncthreads();
-      merge(target, CF::NSLOT);
-      __syncthreads();
-      qa = qb;
-    } while (qa < qe);
+    }
   }
-  flush_all();
+  if (jw != INT_MIN)
+    for (int k = 0; k < NS; ++k) slide();
 }
 
 template<int NS>
@@ -298,9 +315,9 @@ static cudaError_t launch_spread_ns(const PointSet<float> &pts, const GridGeom<f
   a.g   = g;
   constexpr int rows = TableRows<NS>::value;
   for (int k = 0; k < rows; ++k)
-    for (int j = 0; j < NS; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const int src       = k - (rows - nc);
-      a.tab.c[k * NS + j] = src >= 0 ? coef[src * NS + j] : 0.f;
+      a.tab.c[k * 8 + j]  = (src >= 0 && j < NS) ? coef[src * NS + j] : 0.f;
     }
   a.c_in  = c_in;
   a.c_out = nullptr;
@@ -308,14 +325,19 @@ static cudaError_t launch_spread_ns(const PointSet<float> &pts, const GridGeom<f
   // cut every tube into y ranges so that there are enough blocks to balance 148 SMs x 4
   const int tubes = g.nb[0] * g.nb[2];
   int nsplit      = 1;
-  while (tubes * nsplit < 148 * 4 * 12 && g.nb[1] / (nsplit * 2) >= 8) nsplit *= 2;
+  while (tubes * nsplit < 148 * 12 * 8 && g.nb[1] / (nsplit * 2) >= 8) nsplit *= 2;
   a.nsplit = nsplit;
   a.ypi    = (g.nb[1] + nsplit - 1) / nsplit;
+  a.dbg    = getenv("B200_SWEEP_DBG") ? atoi(getenv("B200_SWEEP_DBG")) : 0;
+  if (getenv("B200_SWEEP_NSPLIT")) {
+    a.nsplit = atoi(getenv("B200_SWEEP_NSPLIT"));
+    a.ypi    = (g.nb[1] + a.nsplit - 1) / a.nsplit;
+  }
   auto kern = k_spread3_sweep<NS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)CF::BYTES);
   if (e != cudaSuccess) return e;
-  kern<<<tubes * nsplit, CF::NT, CF::BYTES, st>>>(a);
+  kern<<<tubes * a.nsplit, 32, CF::BYTES, st>>>(a);
   return cudaGetLastError();
 }
 
