@@ -27,28 +27,30 @@ __device__ __forceinline__ float2 fmul2_s(float s, float2 w) {
 }
 
 template<int NS> struct SweepCfg {
-  static constexpr int HL    = NS / 2;                 // cells left of the bin a stencil can reach
-  static constexpr int ROW   = kBinX + NS;             // cells of one register row
-  static constexpr int PAD   = HL & 1;                 // tile x origin 16*i1-HL-PAD is even
-  static constexpr int PITCH = (ROW + PAD + 1) & ~1;   // cells of one tile row (even)
-  static constexpr int SP    = 26;                     // staging row pitch in cells (bank spread)
-  static constexpr int ZT    = kBinZ + NS;             // z rows of the tube tile
-  static constexpr int BQ    = 4;                      // lane groups along z
-  static constexpr int RZ    = (ZT + BQ - 1) / BQ;     // z rows per lane: z = bq + BQ*m
-  static constexpr int ZS    = RZ * BQ;                // z row slots (>= ZT)
-  static constexpr int NJB   = kBinY + 1;              // y stencil starts inside one bin
-  static constexpr int CH    = 64;                     // points per chunk (records in flight)
-  static constexpr int LCAP  = 512;                    // points per sorted batch of one bin
-  static constexpr int RECW  = 36;                     // words per point record
-  // record: [0,NS) phi_x  [7] x offset | jb<<8  [8,8+NS) phi_y  [16+4*bq+m] phi_z of row slot
-  //         (bq,m)  [32,33] strength
-  static constexpr size_t STAGE_BYTES = (size_t)ZS * SP * sizeof(float2);
-  static constexpr size_t REC_BYTES   = (size_t)CH * RECW * sizeof(float);
+  static constexpr int HL   = NS / 2;               // cells left of a bin a stencil can reach
+  static constexpr int W    = 8;                    // x rows of the register window
+  static constexpr int BQ   = 4;                    // lane groups along z
+  static constexpr int YR   = kBinY + NS;           // cells of one register row (along y)
+  static constexpr int ZT   = kBinZ + NS;           // z rows of the tile
+  static constexpr int RZ   = (ZT + BQ - 1) / BQ;   // z rows per lane: z = bq + BQ*m
+  static constexpr int NG   = kBinX / 2 + 1;        // window positions per bin (steps of 2 cells)
+  static constexpr int NJB  = kBinY + 1;            // y stencil starts inside one bin
+  static constexpr int XB   = 4;                    // window origin of bin i1 is kBinX*i1 - XB
+  static constexpr int SX   = 4;                    // x columns collected before a flush
+  static constexpr int NRED = (ZT * YR * (SX / 2) + 31) / 32;  // flush iterations per lane
+  static constexpr int CH   = 64;                   // points per chunk (records in flight)
+  static constexpr int LCAP = 512;                  // points per sorted batch of one bin
+  static constexpr int RECW = 36;                   // words per point record
+  // record: [0,NS) phi_y  [7] key (g<<4 | jb)  [8,16) phi_x rotated so that word 8+a is the
+  //         weight of the window row x = a (mod 8)  [16+4*bq+m] phi_z of tile row bq+4m
+  //         [32,33] strength
+  static constexpr size_t STAGE_BYTES = (size_t)NRED * 32 * sizeof(float4);
+  static constexpr size_t REC_BYTES   = (size_t)(CH + 1) * RECW * sizeof(float);
   static constexpr size_t LIST_BYTES  = (size_t)LCAP * sizeof(uint16_t);
-  static constexpr size_t BYTES       = STAGE_BYTES + REC_BYTES + LIST_BYTES + 64;
-  static_assert(PITCH <= SP, "staging pitch");
-  static_assert(NS * BQ <= 32, "lane map");
-  static_assert(NS <= 7 && RZ <= 3, "record layout");
+  static constexpr size_t CNT_BYTES   = 64 * sizeof(int);
+  static constexpr size_t BYTES       = STAGE_BYTES + REC_BYTES + LIST_BYTES + CNT_BYTES;
+  static_assert(NS + 1 <= W, "two stencil starts must fit the window");
+  static_assert(HL <= XB && NS <= 7 && RZ <= 3 && NG * NJB <= 64, "layout");
 };
 
 // Horner table padded to 8 columns so that two neighbouring panels form one aligned pair:
@@ -79,8 +81,8 @@ template<int NS> struct SweepArgs {
   const float2 *c_in;
   float2 *c_out;
   float2 *fw;
-  int nsplit;  // y ranges per tube
-  int ypi;     // y bins per item
+  int nsplit;  // work items per row of bins
+  int ypi;     // x bins per item
   int dbg;     // experiment switches (0 in production)
 };
 
@@ -89,36 +91,17 @@ __device__ __forceinline__ int pmod(int v, int n) {
   return r < 0 ? r + n : r;
 }
 
-// one point's contribution for a compile-time x offset: NS packed FMAs per owned row
-template<int NS, int XO>
-__device__ __forceinline__ void row_update(float2 (&acc)[SweepCfg<NS>::RZ][SweepCfg<NS>::ROW],
-                                           const float (&kx)[8], const float2 (&w)[SweepCfg<NS>::RZ]) {
-#pragma unroll
-  for (int r = 0; r < SweepCfg<NS>::RZ; ++r)
-#pragma unroll
-    for (int t = 0; t < NS; ++t) acc[r][XO + t] = ffma2_s(kx[t], w[r], acc[r][XO + t]);
-}
-
+// Sort key of a point inside bin (i1, i2): window position g and y stencil start jb.
 template<int NS>
-__device__ __forceinline__ void row_update_switch(
-    int xo, float2 (&acc)[SweepCfg<NS>::RZ][SweepCfg<NS>::ROW], const float (&kx)[8],
-    const float2 (&w)[SweepCfg<NS>::RZ]) {
-  switch (xo) {
-#define B200_XO(k) case k: row_update<NS, k>(acc, kx, w); break;
-    B200_XO(0) B200_XO(1) B200_XO(2) B200_XO(3) B200_XO(4) B200_XO(5) B200_XO(6) B200_XO(7)
-    B200_XO(8) B200_XO(9) B200_XO(10) B200_XO(11) B200_XO(12) B200_XO(13) B200_XO(14)
-    B200_XO(15) B200_XO(16)
-#undef B200_XO
-  default: __builtin_unreachable();
-  }
-}
-
-// y stencil start of a point relative to the first one possible in y bin i2, in [0, kBinY]
-template<int NS> __device__ __forceinline__ int y_bucket(float y, float nf2_t, int i2) {
-  int j0;
-  float y1;
-  stencil_start<float, NS>(fold_rescale<float>(y, nf2_t), j0, y1);
-  return min(max(j0 - (kBinY * i2 - SweepCfg<NS>::HL), 0), kBinY);
+__device__ __forceinline__ int point_key(const SweepArgs<NS> &a, uint32_t q, int i1, int i2) {
+  using CF = SweepCfg<NS>;
+  int i0, j0;
+  float t;
+  stencil_start<float, NS>(fold_rescale<float>(a.pts.xs[q], a.g.nf_t[0]), i0, t);
+  stencil_start<float, NS>(fold_rescale<float>(a.pts.ys[q], a.g.nf_t[1]), j0, t);
+  const int g  = min(max((i0 - (kBinX * i1 - CF::XB)) >> 1, 0), CF::NG - 1);
+  const int jb = min(max(j0 - (kBinY * i2 - CF::HL), 0), kBinY);
+  return g * CF::NJB + jb;
 }
 
 // Thread-per-point preparation: fold, stencil starts, windows, strength -> record.
@@ -131,34 +114,31 @@ __device__ __forceinline__ void make_record(const SweepArgs<NS> &a, uint32_t q, 
   int i0;
   float x1;
   float kv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  stencil_start<float, NS>(fold_rescale<float>(__ldcs(a.pts.ys + q), a.g.nf_t[1]), i0, x1);
-  eval_window2<NS>(a.tab, x1, kv);
-  *reinterpret_cast<float4 *>(rec + 8)  = make_float4(kv[0], kv[1], kv[2], kv[3]);
-  *reinterpret_cast<float4 *>(rec + 12) = make_float4(kv[4], kv[5], kv[6], 0.f);
-  const int jb = min(max(i0 - (kBinY * i2 - CF::HL), 0), kBinY);
   stencil_start<float, NS>(fold_rescale<float>(__ldcs(a.pts.xs + q), a.g.nf_t[0]), i0, x1);
   eval_window2<NS>(a.tab, x1, kv);
-  const int xo = min(max(i0 - (kBinX * i1 - CF::HL), 0), kBinX);
-  kv[7]        = __int_as_float(xo | (jb << 8));
+  i0 = min(max(i0, kBinX * i1 - CF::XB), kBinX * i1 - CF::XB + 2 * CF::NG - 1);
+  const int g = (i0 - (kBinX * i1 - CF::XB)) >> 1;
+  // rotate: the weight of stencil cell t belongs to the window row x = i0 + t (mod 8)
+#pragma unroll
+  for (int t = 0; t < 8; ++t) rec[8 + ((i0 + t) & 7)] = t < NS ? kv[t] : 0.f;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) kv[s] = 0.f;
+  stencil_start<float, NS>(fold_rescale<float>(__ldcs(a.pts.ys + q), a.g.nf_t[1]), i0, x1);
+  eval_window2<NS>(a.tab, x1, kv);
+  const int jb = min(max(i0 - (kBinY * i2 - CF::HL), 0), kBinY);
+  kv[7]        = __int_as_float((g << 4) | jb);
   *reinterpret_cast<float4 *>(rec)     = make_float4(kv[0], kv[1], kv[2], kv[3]);
   *reinterpret_cast<float4 *>(rec + 4) = make_float4(kv[4], kv[5], kv[6], kv[7]);
   stencil_start<float, NS>(fold_rescale<float>(__ldcs(a.pts.zs + q), a.g.nf_t[2]), i0, x1);
   eval_window2<NS>(a.tab, x1, kv);
   // z stencil start relative to the tile's first z row, in [0, kBinZ]
   const int k0 = min(max(i0 - (kBinZ * i3 - CF::HL), 0), kBinZ);
-  // window value of tile row z = bq + BQ*m goes to word 16 + 4*bq + m
+  // tile row z = k0 + t lives in word 16 + 4*(z & 3) + (z >> 2)
 #pragma unroll
-  for (int bq = 0; bq < CF::BQ; ++bq) {
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int bq = 0; bq < CF::BQ; ++bq)
+    *reinterpret_cast<float4 *>(rec + 16 + 4 * bq) = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int m = 0; m < CF::RZ; ++m) {
-      const int z = bq + CF::BQ * m;
-#pragma unroll
-      for (int s = 0; s <= kBinZ; ++s)
-        if (z - s >= 0 && z - s < NS) v[m] = (k0 == s) ? kv[z - s] : v[m];
-    }
-    *reinterpret_cast<float4 *>(rec + 16 + 4 * bq) = make_float4(v[0], v[1], v[2], v[3]);
-  }
+  for (int t = 0; t < NS; ++t) rec[16 + 4 * ((k0 + t) & 3) + ((k0 + t) >> 2)] = kv[t];
   *reinterpret_cast<float2 *>(rec + 32) = c;
 }
 
@@ -166,143 +146,196 @@ __device__ __forceinline__ void sts64(uint32_t addr, float2 v) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
 
-// One warp per work item: a tube (x bin i1, z bin i3) over the y bins [yb0, yb1).
+// what one lane needs of one record
+struct SpreadRec {
+  float4 k0, k1;  // phi_y[0..6], key
+  float wx;       // phi_x of this lane's window row
+  float4 fz;      // phi_z of this lane's tile rows
+  float2 c;
+};
+
+template<int NS, int JB>
+__device__ __forceinline__ void spread_update(float2 (&acc)[SweepCfg<NS>::RZ][SweepCfg<NS>::YR],
+                                              const SpreadRec &r) {
+  using CF = SweepCfg<NS>;
+  const float ky[8] = {r.k0.x, r.k0.y, r.k0.z, r.k0.w, r.k1.x, r.k1.y, r.k1.z, 0.f};
+  const float fz[4] = {r.fz.x, r.fz.y, r.fz.z, r.fz.w};
+  const float2 cw   = fmul2_s(r.wx, r.c);
+#pragma unroll
+  for (int m = 0; m < CF::RZ; ++m) {
+    const float2 w = fmul2_s(fz[m], cw);
+#pragma unroll
+    for (int t = 0; t < NS; ++t) acc[m][JB + t] = ffma2_s(ky[t], w, acc[m][JB + t]);
+  }
+}
+
+// One warp per work item: the row of bins (i2, i3), swept along x.
 template<int NS>
-__global__ void __launch_bounds__(32, 12) k_spread3_sweep(const SweepArgs<NS> a) {
+__global__ void __launch_bounds__(32, 16) k_spread3_sweep(const SweepArgs<NS> a) {
   using CF = SweepCfg<NS>;
   extern __shared__ __align__(16) unsigned char smem[];
-  float2 *stage  = reinterpret_cast<float2 *>(smem);
+  float4 *stage4 = reinterpret_cast<float4 *>(smem);
   float *rec     = reinterpret_cast<float *>(smem + CF::STAGE_BYTES);
   uint16_t *list = reinterpret_cast<uint16_t *>(smem + CF::STAGE_BYTES + CF::REC_BYTES);
   int *cnt       = reinterpret_cast<int *>(smem + CF::STAGE_BYTES + CF::REC_BYTES + CF::LIST_BYTES);
 
   const int lane = threadIdx.x;
-  const int la = lane / CF::BQ, bq = lane % CF::BQ;  // la >= NS: spare lane
+  const int la = lane >> 2, bq = lane & 3;
   const int nb1 = a.g.nb[0], nb2 = a.g.nb[1];
-  const int tube = blockIdx.x / a.nsplit, part = blockIdx.x % a.nsplit;
-  const int i1 = tube % nb1, i3 = tube / nb1;
-  const int yb0 = part * a.ypi, yb1 = min(nb2, yb0 + a.ypi);
+  const int row = blockIdx.x / a.nsplit, part = blockIdx.x % a.nsplit;
+  const int i2 = row % nb2, i3 = row / nb2;
+  const int xb0 = part * a.ypi, xb1 = min(nb1, xb0 + a.ypi);
   const int nf1 = a.g.nf[0], nf2 = a.g.nf[1], nf3 = a.g.nf[2];
-  const int x0t = kBinX * i1 - CF::HL - CF::PAD;  // tile origin (even)
-  const int z0t = kBinZ * i3 - CF::HL;
 
-  // staging starts zeroed: the pad cells of every row are never written afterwards
-  for (int i = lane; i < (int)(CF::STAGE_BYTES / sizeof(float2)); i += 32)
-    stage[i] = float2{0.f, 0.f};
-
-  float2 acc[CF::RZ][CF::ROW];
+  // fine-grid offset of the (z, y) line each flush iteration of this lane serves
+  uint32_t lineoff[CF::NRED];
 #pragma unroll
-  for (int r = 0; r < CF::RZ; ++r)
-#pragma unroll
-    for (int c = 0; c < CF::ROW; ++c) acc[r][c] = float2{0.f, 0.f};
-  int jw = INT_MIN;  // first y row of the register window; INT_MIN = window empty
+  for (int k = 0; k < CF::NRED; ++k) {
+    const int yz = (lane + 32 * k) >> 1, z = yz / CF::YR, yc = yz - z * CF::YR;
+    const int gz = wrap_index(kBinZ * i3 - CF::HL + z, nf3),
+              gy = wrap_index(kBinY * i2 - CF::HL + yc, nf2);
+    lineoff[k] = z < CF::ZT ? ((uint32_t)gz * (uint32_t)nf2 + (uint32_t)gy) * (uint32_t)nf1
+                            : 0xffffffffu;
+  }
 
+  float2 acc[CF::RZ][CF::YR];
+#pragma unroll
+  for (int m = 0; m < CF::RZ; ++m)
+#pragma unroll
+    for (int c = 0; c < CF::YR; ++c) acc[m][c] = float2{0.f, 0.f};
+  constexpr int NONE = INT_MIN;
+  int jw = NONE;  // first x row of the register window (even); NONE = window empty
+  int sbase = 0;  // x of staging column 0 (multiple of 4)
+  int stlo  = 0;  // first staging column that holds data
+
+  // staging cell (z, yc, xs) is float2 index (z*YR + yc)*SX + xs
   const uint32_t my_stage =
-      (uint32_t)__cvta_generic_to_shared(stage + (size_t)bq * CF::SP + CF::PAD);
-  __syncwarp();
+      (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)(bq * CF::YR * CF::SX * sizeof(float2));
 
-  // The window's first row leaves: its owners park it in the staging tile, then the whole warp
-  // adds the tile row to the fine grid with 16-byte vector reductions.
+  // add staging columns [stlo, hi) to the fine grid, 16 bytes (two x cells) per reduction
+  auto flush_stage = [&](int hi) {
+    __syncwarp();
+    const int pr = lane & 1;
+    if (2 * pr >= stlo && 2 * pr < hi) {
+      const uint32_t gx = (uint32_t)wrap_index(sbase + 2 * pr, nf1);
+#pragma unroll
+      for (int k = 0; k < CF::NRED; ++k) {
+        if (lineoff[k] != 0xffffffffu) {
+          const float4 v = stage4[lane + 32 * k];
+          if ((v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) && !(a.dbg & 1))
+            atomicAdd(reinterpret_cast<float4 *>(a.fw + lineoff[k] + gx), v);
+        }
+      }
+    }
+    __syncwarp();
+  };
+  // the window's first two x rows leave: their owners park them in the staging tile
   auto slide = [&]() {
-    if (la == pmod(jw, NS)) {
+    const int r0 = jw & 7, r1 = (jw + 1) & 7;
+    if (la == r0 || la == r1) {
+      const uint32_t dst = my_stage + (uint32_t)((jw - sbase + (la == r1 ? 1 : 0)) * sizeof(float2));
 #pragma unroll
       for (int m = 0; m < CF::RZ; ++m)
 #pragma unroll
-        for (int c = 0; c < CF::ROW; ++c) {
-          sts64(my_stage + (uint32_t)((m * CF::BQ * CF::SP + c) * sizeof(float2)), acc[m][c]);
+        for (int c = 0; c < CF::YR; ++c) {
+          if (m * CF::BQ < CF::ZT - 3 || bq + m * CF::BQ < CF::ZT)
+            sts64(dst + (uint32_t)(((m * CF::BQ * CF::YR) + c) * CF::SX * sizeof(float2)), acc[m][c]);
           acc[m][c] = float2{0.f, 0.f};
         }
     }
-    __syncwarp();
-    constexpr int NXP = CF::PITCH / 2;
-    const int gy      = wrap_index(jw, nf2);
-    for (int idx = lane; idx < CF::ZT * NXP; idx += 32) {
-      const int z = idx / NXP, xp = idx - z * NXP;
-      const float4 v = *reinterpret_cast<const float4 *>(stage + (size_t)z * CF::SP + 2 * xp);
-      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
-        const int gx = wrap_index(x0t + 2 * xp, nf1), gz = wrap_index(z0t + z, nf3);
-        if (!(a.dbg & 1))
-          atomicAdd(reinterpret_cast<float4 *>(a.fw + ((size_t)gz * nf2 + gy) * (size_t)nf1 + gx), v);
-      }
+    jw += 2;
+    if (jw - sbase == CF::SX) {
+      flush_stage(CF::SX);
+      sbase += CF::SX;
+      stlo = 0;
     }
-    __syncwarp();
-    ++jw;
   };
-  // move the window so that it starts at row j0 (never backwards unless it is emptied first)
-  auto advance_to = [&](int j0) {
-    if (jw == INT_MIN) {
-      jw = j0;
-      return;
+  auto empty_window = [&]() {
+    if (jw == NONE) return;
+    for (int k = 0; k < CF::W / 2; ++k) slide();
+    if (jw - sbase > stlo) flush_stage(jw - sbase);
+    jw = NONE;
+  };
+  auto advance_to = [&](int x) {
+    if (jw != NONE && (x < jw || x - jw >= CF::W)) empty_window();
+    if (jw == NONE) {
+      jw    = x;
+      sbase = x & ~(CF::SX - 1);
+      stlo  = x - sbase;
     }
-    if (j0 < jw || j0 - jw >= NS) {  // rewind or long jump: empty the window
-      for (int k = 0; k < NS; ++k) slide();
-      jw = j0;
-      return;
-    }
-    while (jw < j0) slide();
+    while (jw < x) slide();
   };
 
-  for (int i2 = yb0; i2 < yb1; ++i2) {
+  for (int i1 = xb0; i1 < xb1; ++i1) {
     const uint32_t bin = (uint32_t)i1 + (uint32_t)nb1 * ((uint32_t)i2 + (uint32_t)nb2 * (uint32_t)i3);
     const uint32_t qs = a.pts.binstart[bin], qe = a.pts.binstart[bin + 1];
-    const int target = kBinY * i2 - CF::HL;
+    const int xbase = kBinX * i1 - CF::XB;
     for (uint32_t q0 = qs; q0 < qe; q0 += CF::LCAP) {
       const int n = (int)min((uint32_t)CF::LCAP, qe - q0);
-      // ---- sort this batch of the bin by y stencil start (counting sort, 5 buckets)
-      if (lane < 8) cnt[lane] = 0;
+      // ---- counting sort of this batch by (window position, y stencil start)
+      cnt[lane] = 0, cnt[lane + 32] = 0;
+      __syncwarp();
+      for (int k = lane; k < n; k += 32) atomicAdd(&cnt[point_key<NS>(a, q0 + k, i1, i2)], 1);
+      __syncwarp();
+      {
+        const int v0 = cnt[2 * lane], v1 = cnt[2 * lane + 1];
+        int incl = v0 + v1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += up;
+        }
+        __syncwarp();
+        cnt[2 * lane]     = incl - v0 - v1;
+        cnt[2 * lane + 1] = incl - v1;
+      }
       __syncwarp();
       for (int k = lane; k < n; k += 32)
-        atomicAdd(&cnt[y_bucket<NS>(a.pts.ys[q0 + k], a.g.nf_t[1], i2)], 1);
-      __syncwarp();
-      if (lane == 0) {
-        int run = 0;
-        for (int b = 0; b < CF::NJB; ++b) {
-          const int c = cnt[b];
-          cnt[b]      = run;
-          run += c;
-        }
-      }
-      __syncwarp();
-      for (int k = lane; k < n; k += 32) {
-        const int pos = atomicAdd(&cnt[y_bucket<NS>(a.pts.ys[q0 + k], a.g.nf_t[1], i2)], 1);
-        list[pos]     = (uint16_t)k;
-      }
+        list[atomicAdd(&cnt[point_key<NS>(a, q0 + k, i1, i2)], 1)] = (uint16_t)k;
       __syncwarp();
       for (int c0 = 0; c0 < n; c0 += CF::CH) {
         const int nc = min(CF::CH, n - c0);
-        // ---- records for the next nc points in sorted order
+        // ---- records of the next nc points in sorted order, then a sentinel
         for (int k = lane; k < nc; k += 32)
           make_record<NS, true>(a, q0 + list[c0 + k], rec + k * CF::RECW, i1, i2, i3);
+        if (lane == 0) rec[nc * CF::RECW + 7] = __int_as_float(-1);
         __syncwarp();
-        // ---- accumulate
-        int cur_jb = -1, ta = 0;
-        for (int p = 0; p < ((a.dbg & 2) ? 0 : nc); ++p) {
+        // ---- accumulate: runs of equal key share the window position and the y offset
+        auto load = [&](int p) {
           const float *rp = rec + p * CF::RECW;
-          const float4 k0 = *reinterpret_cast<const float4 *>(rp);
-          const float4 k1 = *reinterpret_cast<const float4 *>(rp + 4);
-          const int meta  = __float_as_int(k1.w);
-          const int jb    = meta >> 8;
-          if (jb != cur_jb) {  // warp-uniform
-            cur_jb = jb;
-            advance_to(target + jb);
-            ta = la < NS ? pmod(la - (target + jb), NS) : 0;
+          SpreadRec r;
+          r.k0 = *reinterpret_cast<const float4 *>(rp);
+          r.k1 = *reinterpret_cast<const float4 *>(rp + 4);
+          r.wx = rp[8 + la];
+          r.fz = *reinterpret_cast<const float4 *>(rp + 16 + 4 * bq);
+          r.c  = *reinterpret_cast<const float2 *>(rp + 32);
+          return r;
+        };
+        int p        = 0;
+        SpreadRec nx = load(0);
+        while (!(a.dbg & 2)) {
+          const int key = __float_as_int(nx.k1.w);
+          if (key < 0) break;
+          advance_to(xbase + 2 * (key >> 4));
+#define B200_RUN(J)                                       \
+  case J:                                                 \
+    do {                                                  \
+      const SpreadRec cu = nx;                            \
+      nx                 = load(++p);                     \
+      spread_update<NS, J>(acc, cu);                      \
+    } while (__float_as_int(nx.k1.w) == key);             \
+    break;
+          switch (key & 15) {
+            B200_RUN(0) B200_RUN(1) B200_RUN(2) B200_RUN(3) B200_RUN(4)
+          default: __builtin_unreachable();
           }
-          const float wy  = rp[8 + ta];
-          const float4 fz = *reinterpret_cast<const float4 *>(rp + 16 + 4 * bq);
-          const float2 cw = fmul2_s(wy, *reinterpret_cast<const float2 *>(rp + 32));
-          const float kx[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, 0.f};
-          float2 w[CF::RZ];
-          w[0] = fmul2_s(fz.x, cw);
-          w[1] = fmul2_s(fz.y, cw);
-          if (CF::RZ > 2) w[CF::RZ - 1] = fmul2_s(fz.z, cw);
-          row_update_switch<NS>(meta & 0xff, acc, kx, w);
+#undef B200_RUN
         }
         __syncwarp();
       }
     }
   }
-  if (jw != INT_MIN)
-    for (int k = 0; k < NS; ++k) slide();
+  empty_window();
 }
 
 template<int NS>
@@ -322,22 +355,22 @@ static cudaError_t launch_spread_ns(const PointSet<float> &pts, const GridGeom<f
   a.c_in  = c_in;
   a.c_out = nullptr;
   a.fw    = fw;
-  // cut every tube into y ranges so that there are enough blocks to balance 148 SMs x 4
-  const int tubes = g.nb[0] * g.nb[2];
-  int nsplit      = 1;
-  while (tubes * nsplit < 148 * 12 * 8 && g.nb[1] / (nsplit * 2) >= 8) nsplit *= 2;
+  // one warp per row of bins (i2, i3); rows are cut along x only when there are too few of them
+  const int nrows = g.nb[1] * g.nb[2];
+  int nsplit     = 1;
+  while (nrows * nsplit < 148 * 16 * 4 && g.nb[0] / (nsplit * 2) >= 2) nsplit *= 2;
   a.nsplit = nsplit;
-  a.ypi    = (g.nb[1] + nsplit - 1) / nsplit;
+  a.ypi    = (g.nb[0] + nsplit - 1) / nsplit;
   a.dbg    = getenv("B200_SWEEP_DBG") ? atoi(getenv("B200_SWEEP_DBG")) : 0;
   if (getenv("B200_SWEEP_NSPLIT")) {
     a.nsplit = atoi(getenv("B200_SWEEP_NSPLIT"));
-    a.ypi    = (g.nb[1] + a.nsplit - 1) / a.nsplit;
+    a.ypi    = (g.nb[0] + a.nsplit - 1) / a.nsplit;
   }
   auto kern = k_spread3_sweep<NS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)CF::BYTES);
   if (e != cudaSuccess) return e;
-  kern<<<tubes * a.nsplit, 32, CF::BYTES, st>>>(a);
+  kern<<<nrows * a.nsplit, 32, CF::BYTES, st>>>(a);
   return cudaGetLastError();
 }
 
