@@ -39,6 +39,7 @@ template struct DevBuf<double>;
 template struct DevBuf<float2>;
 template struct DevBuf<double2>;
 template struct DevBuf<uint32_t>;
+template struct DevBuf<SweepItem>;
 
 DeviceGuard::DeviceGuard(int dev) {
   int count = 0;
@@ -222,6 +223,11 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
   launch_bin_bounds(sorted_keys, m, geom.nbins, binstart_.p, st);
   launch_gather_coords<T>(dim, x, y, z, sidx_.p, m, xs_.p, ys_.p, zs_.p, st);
 
+  // 3D float with a supported width: refine the order inside the bins for the sweep kernels
+  swept_ = std::is_same<T, float>::value && dim == 3 && sweep3_supported(ns) && opts.sweep &&
+           nf[0] % 2 == 0 && M > 0;
+  if (swept_) refine_for_sweep(scan_tmp.p);
+
   // subproblem list: every bin in chunks of at most maxsub points
   nsubs.alloc(geom.nbins);
   substart.alloc((size_t)geom.nbins + 1);
@@ -239,6 +245,32 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
                     sub_off_.p, st);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(st));  // scratch buffers are freed on return
+}
+
+static void refine_impl(int ns, float *xs, float *ys, float *zs, uint32_t *sidx,
+                        const uint32_t *binstart, const GridGeom<float> &g, cudaStream_t st) {
+  launch_refine_bins3(ns, xs, ys, zs, sidx, binstart, g, st);
+}
+static void refine_impl(int, double *, double *, double *, uint32_t *, const uint32_t *,
+                        const GridGeom<double> &, cudaStream_t) {}
+template<class T> void Engine<T>::refine_for_sweep(uint32_t *scan_tmp) {
+  cudaStream_t st = opts.stream;
+  refine_impl(ns, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, st);
+  const uint32_t nrows = (uint32_t)geom.nb[1] * (uint32_t)geom.nb[2];
+  DevBuf<uint32_t> nit, itstart;
+  nit.alloc(nrows);
+  itstart.alloc((size_t)nrows + 1);
+  launch_row_item_count(binstart_.p, nrows, (uint32_t)geom.nb[0], kSweepItemPoints, nit.p, st);
+  exclusive_scan_u32(nit.p, itstart.p, nrows, scan_tmp, st);
+  uint32_t total = 0;
+  CU(cudaMemcpyAsync(&total, itstart.p + nrows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  nitems_ = total;
+  items_.alloc(std::max<uint32_t>(total, 1));
+  if (total)
+    launch_row_item_fill(binstart_.p, itstart.p, nrows, (uint32_t)geom.nb[0], kSweepItemPoints,
+                         items_.p, st);
+  CU(cudaStreamSynchronize(st));  // nit / itstart are freed on return
 }
 
 template<class T>
@@ -267,23 +299,25 @@ void Engine<T>::setpts(int64_t M_, const T *x, const T *y, const T *z, int64_t N
 }
 
 // ------------------------------------------------------------------ execute
-// The tube-sweep kernels (sweep3d.cuh) take 3D single-precision grids whose x rows can be
-// addressed in aligned 16-byte pairs.
+// The row-sweep kernels (sweep3d.cuh) take 3D single-precision grids whose x lines can be
+// addressed in aligned 16-byte pairs; setpts has then refined the bin order for them.
 template<class T> bool Engine<T>::use_sweep3(const void *grid) const {
-  return std::is_same<T, float>::value && dim == 3 && sweep3_supported(ns) && opts.sweep &&
-         nf[0] % 2 == 0 && (reinterpret_cast<uintptr_t>(grid) & 15) == 0;
+  return swept_ && (reinterpret_cast<uintptr_t>(grid) & 15) == 0;
 }
-static cudaError_t sweep_spread_impl(int ns, const PointSet<float> &pts, const GridGeom<float> &g,
-                                     int nc, const float *coef, const float2 *c, float2 *fw,
-                                     cudaStream_t st) {
-  return launch_spread3_sweep(ns, pts, g, nc, coef, c, fw, st);
+static cudaError_t sweep_impl(bool spread, int ns, const SweepPoints &pts,
+                              const GridGeom<float> &g, int nc, const float *coef, float2 *c,
+                              float2 *fw, cudaStream_t st) {
+  return spread ? launch_spread3_sweep(ns, pts, g, nc, coef, c, fw, st)
+                : launch_interp3_sweep(ns, pts, g, nc, coef, c, fw, st);
 }
-static cudaError_t sweep_spread_impl(int, const PointSet<double> &, const GridGeom<double> &, int,
-                                     const double *, const double2 *, double2 *, cudaStream_t) {
+static cudaError_t sweep_impl(bool, int, const SweepPoints &, const GridGeom<double> &, int,
+                              const double *, double2 *, double2 *, cudaStream_t) {
   return cudaErrorInvalidValue;
 }
-template<class T> cudaError_t Engine<T>::sweep_spread(const PointSet<T> &pts, const C *c, C *fw) {
-  return sweep_spread_impl(ns, pts, geom, nc, coef.data(), c, fw, opts.stream);
+template<class T> cudaError_t Engine<T>::sweep_run(bool spread, C *c, C *fw) {
+  SweepPoints sp{reinterpret_cast<const float *>(xs_.p), reinterpret_cast<const float *>(ys_.p),
+                 reinterpret_cast<const float *>(zs_.p), sidx_.p, items_.p, nitems_};
+  return sweep_impl(spread, ns, sp, geom, nc, coef.data(), c, fw, opts.stream);
 }
 template<class T> void Engine<T>::run_spread(const C *c, C *fw) {
   if (nsub == 0) return;
@@ -291,7 +325,7 @@ template<class T> void Engine<T>::run_spread(const C *c, C *fw) {
                   (uint32_t)opts.maxsub};
   cudaError_t e;
   if (use_sweep3(fw))
-    e = sweep_spread(pts, c, fw);
+    e = sweep_run(true, const_cast<C *>(c), fw);
   else if (dim == 1)
     e = launch_spreadinterp<T, 1>(true, ns, pts, geom, nc, coef.data(), c, nullptr, fw, opts.stream);
   else if (dim == 2)
@@ -308,7 +342,9 @@ template<class T> void Engine<T>::run_interp(C *c, const C *fw) {
                   (uint32_t)opts.maxsub};
   cudaError_t e;
   C *fwm = const_cast<C *>(fw);
-  if (dim == 1)
+  if (use_sweep3(fw))
+    e = sweep_run(false, c, fwm);
+  else if (dim == 1)
     e = launch_spreadinterp<T, 1>(false, ns, pts, geom, nc, coef.data(), nullptr, c, fwm, opts.stream);
   else if (dim == 2)
     e = launch_spreadinterp<T, 2>(false, ns, pts, geom, nc, coef.data(), nullptr, c, fwm, opts.stream);
@@ -402,6 +438,15 @@ template<class T> void Engine<T>::copy_sort_to_host(uint32_t *out) const {
   if (M == 0) return;
   cudaStreamSynchronize(opts.stream);
   cuda_check(cudaMemcpy(out, sidx_.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToHost), "copy sort");
+  if (swept_) {
+    // The sweep kernels re-order points inside each bin; the reference's stable counting sort
+    // leaves them in ascending index order (include/finufft/spread.hpp:559-581), which is
+    // restored here for inspection.
+    std::vector<uint32_t> bs((size_t)geom.nbins + 1);
+    cuda_check(cudaMemcpy(bs.data(), binstart_.p, sizeof(uint32_t) * bs.size(),
+                          cudaMemcpyDeviceToHost), "copy binstart");
+    for (uint32_t b = 0; b < geom.nbins; ++b) std::sort(out + bs[b], out + bs[b + 1]);
+  }
 }
 template<class T> void Engine<T>::copy_phihat_to_host(int d, T *out) const {
   cudaStreamSynchronize(opts.stream);

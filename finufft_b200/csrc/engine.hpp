@@ -95,7 +95,8 @@ template<class T> class Engine {
   void plan_grid();
   void sort_points(const T *x, const T *y, const T *z);
   bool use_sweep3(const void *grid) const;
-  cudaError_t sweep_spread(const PointSet<T> &pts, const C *c, C *fw);
+  cudaError_t sweep_run(bool spread, C *c, C *fw);
+  void refine_for_sweep(uint32_t *scan_tmp);
   void run_spread(const C *c, C *fw);
   void run_interp(C *c, const C *fw);
   void spread_path(C *c, C *fk, int fsign);
@@ -115,6 +116,9 @@ template<class T> class Engine {
   // point state
   DevBuf<T> xs_, ys_, zs_;
   DevBuf<uint32_t> sidx_, binstart_, sub_bin_, sub_off_;
+  DevBuf<SweepItem> items_;  // 3D float sweep kernels: work items, refined bin order in use
+  uint32_t nitems_ = 0;
+  bool swept_      = false;
   // type 3
   DevBuf<T> xp_[3], sp_[3];
   DevBuf<C> prephase_, deconv_, cp_;

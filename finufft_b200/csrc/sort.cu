@@ -333,6 +333,123 @@ void launch_sub_fill(const uint32_t *binstart, const uint32_t *substart, uint32_
                                                    sub_off);
 }
 
+// ------------------------------------------------------------------------------ sweep support
+// One warp per bin.  The bin's points (coordinates + index) are pulled into shared memory in
+// batches, ranked by a stable counting sort on key = g*5 + jb (g: x window position inside the
+// bin in steps of two cells, jb: y stencil start inside the bin) and written back in place.
+constexpr int kRefCap = 512, kRefWarps = 4, kRefKeys = 64;
+
+template<int NS>
+__global__ void __launch_bounds__(kRefWarps * 32)
+k_refine_bins3(float *__restrict__ xs, float *__restrict__ ys, float *__restrict__ zs,
+               uint32_t *__restrict__ sidx, const uint32_t *__restrict__ binstart,
+               GridGeom<float> g) {
+  __shared__ float sx[kRefWarps][kRefCap], sy[kRefWarps][kRefCap], sz[kRefWarps][kRefCap];
+  __shared__ uint32_t si[kRefWarps][kRefCap];
+  __shared__ uint16_t spos[kRefWarps][kRefCap];
+  __shared__ int cnt[kRefWarps][kRefKeys];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t nwarps = gridDim.x * kRefWarps;
+  constexpr int HL = NS / 2, XB = 4, NG = kBinX / 2 + 1, NJB = kBinY + 1;
+  for (uint32_t bin = blockIdx.x * kRefWarps + warp; bin < g.nbins; bin += nwarps) {
+    const uint32_t qs = binstart[bin], qe = binstart[bin + 1];
+    if (qe - qs < 2) continue;
+    const int i1 = bin % g.nb[0], i2 = (bin / g.nb[0]) % g.nb[1];
+    for (uint32_t q0 = qs; q0 < qe; q0 += kRefCap) {
+      const int n = (int)min((uint32_t)kRefCap, qe - q0);
+      cnt[warp][lane] = 0, cnt[warp][lane + 32] = 0;
+      __syncwarp();
+      for (int k = lane; k < n; k += 32) {
+        const float x = xs[q0 + k], y = ys[q0 + k];
+        sx[warp][k] = x, sy[warp][k] = y, sz[warp][k] = zs[q0 + k], si[warp][k] = sidx[q0 + k];
+        int i0, j0;
+        float t;
+        stencil_start<float, NS>(fold_rescale<float>(x, g.nf_t[0]), i0, t);
+        stencil_start<float, NS>(fold_rescale<float>(y, g.nf_t[1]), j0, t);
+        const int gg  = min(max((i0 - (kBinX * i1 - XB)) >> 1, 0), NG - 1);
+        const int jb  = min(max(j0 - (kBinY * i2 - HL), 0), kBinY);
+        const int key = gg * NJB + jb;
+        spos[warp][k] = (uint16_t)key;
+        atomicAdd(&cnt[warp][key], 1);
+      }
+      __syncwarp();
+      {  // exclusive scan of the 64 counters, two per lane
+        const int v0 = cnt[warp][2 * lane], v1 = cnt[warp][2 * lane + 1];
+        int incl = v0 + v1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += up;
+        }
+        __syncwarp();
+        cnt[warp][2 * lane]     = incl - v0 - v1;
+        cnt[warp][2 * lane + 1] = incl - v1;
+      }
+      __syncwarp();
+      // stable ranks: rounds of 32 points in order, lanes in order inside a round
+      for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k       = k0 + lane;
+        const bool valid  = k < n;
+        const int key     = valid ? (int)spos[warp][k] : kRefKeys + lane;  // invalid: unique
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const int leader  = __ffs(peers) - 1;
+        int base          = 0;
+        if (valid && lane == leader) base = cnt[warp][key];
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid) spos[warp][k] = (uint16_t)(base + __popc(peers & lt_mask));
+        if (valid && lane == leader) cnt[warp][key] = base + __popc(peers);
+        __syncwarp();
+      }
+      for (int k = lane; k < n; k += 32) {
+        const uint32_t dst = q0 + spos[warp][k];
+        xs[dst] = sx[warp][k], ys[dst] = sy[warp][k], zs[dst] = sz[warp][k], sidx[dst] = si[warp][k];
+      }
+      __syncwarp();
+    }
+  }
+}
+
+void launch_refine_bins3(int ns, float *xs, float *ys, float *zs, uint32_t *sidx,
+                         const uint32_t *binstart, const GridGeom<float> &g, cudaStream_t st) {
+  const int nb = grid_for((g.nbins + kRefWarps - 1) / kRefWarps * 32 * kRefWarps, kRefWarps * 32, 16);
+  switch (ns) {
+#define B200_REF(NSV) \
+  case NSV: k_refine_bins3<NSV><<<nb, kRefWarps * 32, 0, st>>>(xs, ys, zs, sidx, binstart, g); break;
+    B200_REF(2) B200_REF(3) B200_REF(4) B200_REF(5) B200_REF(6) B200_REF(7)
+#undef B200_REF
+  default: break;
+  }
+}
+
+__global__ void k_row_item_count(const uint32_t *__restrict__ binstart, uint32_t nrows,
+                                 uint32_t nb1, uint32_t maxpts, uint32_t *__restrict__ nitems) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
+    const uint32_t n = binstart[(size_t)(r + 1) * nb1] - binstart[(size_t)r * nb1];
+    nitems[r]        = (n + maxpts - 1) / maxpts;
+  }
+}
+__global__ void k_row_item_fill(const uint32_t *__restrict__ binstart,
+                                const uint32_t *__restrict__ itemstart, uint32_t nrows,
+                                uint32_t nb1, uint32_t maxpts, SweepItem *__restrict__ items) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
+    const uint32_t qs = binstart[(size_t)r * nb1], qe = binstart[(size_t)(r + 1) * nb1];
+    uint32_t s = itemstart[r];
+    for (uint32_t q = qs; q < qe; q += maxpts, ++s) items[s] = SweepItem{r, q, min(qe, q + maxpts)};
+  }
+}
+void launch_row_item_count(const uint32_t *binstart, uint32_t nrows, uint32_t nb1,
+                           uint32_t maxpts, uint32_t *nitems, cudaStream_t st) {
+  k_row_item_count<<<grid_for(nrows, 256), 256, 0, st>>>(binstart, nrows, nb1, maxpts, nitems);
+}
+void launch_row_item_fill(const uint32_t *binstart, const uint32_t *itemstart, uint32_t nrows,
+                          uint32_t nb1, uint32_t maxpts, SweepItem *items, cudaStream_t st) {
+  k_row_item_fill<<<grid_for(nrows, 256), 256, 0, st>>>(binstart, itemstart, nrows, nb1, maxpts,
+                                                       items);
+}
+
 __global__ void k_iota(uint32_t *v, uint32_t n) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = i;

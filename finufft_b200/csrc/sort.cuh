@@ -55,4 +55,22 @@ void launch_sub_fill(const uint32_t *binstart, const uint32_t *substart, uint32_
 
 void launch_iota(uint32_t *v, uint32_t n, cudaStream_t st);
 
+// --- 3D sweep support (sweep3d.cuh) --------------------------------------------------------
+// Re-orders the points inside every bin, in place, by (x window position, y stencil start) so
+// that a row of bins read front to back is sorted by x window position.  The order stays a
+// refinement of the bin order: bins keep their ranges.  Stable (ties keep the bin order).
+// ns = kernel width (fixes the stencil start rule ceil(X - ns/2)).
+void launch_refine_bins3(int ns, float *xs, float *ys, float *zs, uint32_t *sidx,
+                         const uint32_t *binstart, const GridGeom<float> &g, cudaStream_t st);
+
+// Work items of the sweep kernels: every row of bins (i2, i3) cut into runs of at most
+// `maxpts` consecutive points.  item = {row, first point, one past last point}.
+struct SweepItem {
+  uint32_t row, qa, qb;
+};
+void launch_row_item_count(const uint32_t *binstart, uint32_t nrows, uint32_t nb1,
+                           uint32_t maxpts, uint32_t *nitems, cudaStream_t st);
+void launch_row_item_fill(const uint32_t *binstart, const uint32_t *itemstart, uint32_t nrows,
+                          uint32_t nb1, uint32_t maxpts, SweepItem *items, cudaStream_t st);
+
 }  // namespace b200
