@@ -42,6 +42,8 @@ WORKLOADS = {
     "c2_t2": (2, (2048, 2048), 100_000_000, 1e-5, "complex64", 1),
     "c4_t1": (1, (512, 512), 10_000_000, 1e-9, "complex128", 8),
 }
+# type 3 (configs[4]): M sources, N = M targets with frequencies of half-width 107.5 per dim
+# (perftest/perftest.cpp:197-202 with N1=N2=N3=215); benched by tools/bench_type3.py
 METRIC = "NU points/sec (spread+FFT+deconv)"
 
 

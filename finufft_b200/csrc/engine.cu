@@ -163,6 +163,10 @@ template<class T> void Engine<T>::plan_grid() {
   if (nbins > 0x7fffffffull) throw Failure{ERR_NDATA_NOTVALID};
   geom.nbins = (uint32_t)nbins;
   if (opts.spreadinterponly) return;
+  if (type == 3) {  // spread grid only: the inner type-2 plan owns the FFT and the series
+    fw_.alloc((size_t)total);
+    return;
+  }
 
   cudaStream_t st = opts.stream;
   for (int d = 0; d < dim; ++d) {  // plan-time, O(nf * ns): host, in the reference's arithmetic

@@ -242,6 +242,39 @@ def test_host_pointer_api(cuda, oracle):
     assert e.value.code == 7
 
 
+@pytest.mark.parametrize("prec,tol", [("f", 1e-5), ("d", 1e-9)])
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_type3_matches_oracle_and_direct_sum(cuda, oracle, prec, tol, dim):
+    """Type 3 (include/finufft/setpts.hpp:163-319, execute.hpp:432-558): device and host entry
+    points against the oracle (2*tol) and the O(NM) direct sum (tolsweep-style threshold)."""
+    import finufft_b200 as F
+    rng = np.random.default_rng(40 + dim)
+    rt, ct = _dt(prec)
+    M, N, ntr = 3000, 2500, 2
+    pts = [rng.uniform(-np.pi, np.pi, M).astype(rt) + rt(0.3 * d) for d in range(dim)]
+    frq = [(rng.uniform(-20, 20, N) + 3.0 * (d + 1)).astype(rt) for d in range(dim)]
+    c = _rand_c(rng, (ntr, M), ct)
+    gp = F.Plan(3, dim, ntr, tol, 1, ct, upsampfac=2.0)
+    gp.setpts(*[cuda.from_numpy(a).cuda() for a in pts],
+              **dict(zip("stu", [cuda.from_numpy(a).cuda() for a in frq])))
+    got = gp.execute(cuda.from_numpy(c).cuda()).cpu().numpy()
+    op = oracle.Plan(3, [1] * dim, 1, ntr, tol, rt, sigma=2.0, dim=dim, nthr=oracle.max_threads())
+    lp, lf = pts[::-1] + [None] * (3 - dim), frq[::-1] + [None] * (3 - dim)
+    op.setpts(lp[0], lp[1], lp[2], lf[0], lf[1], lf[2])
+    want = op.execute(c)
+    assert oracle.relerr(got.reshape(-1), want.reshape(-1)) <= 2 * tol
+    for b in range(ntr):
+        ds = oracle.dirft(3, lp[0], lp[1], lp[2], c[b].astype(np.complex128), 1,
+                          s=lf[0], t=lf[1], u=lf[2])
+        assert oracle.relerr(got[b], ds) <= 10 * tol
+    hp = F.HostPlan(3, dim, ntr, tol, 1, ct, upsampfac=2.0, allow_eps_too_small=1)
+    hp.setpts(*pts, **dict(zip("stu", frq)))
+    hgot = hp.execute(c)
+    assert oracle.relerr(hgot.reshape(-1), got.reshape(-1)) <= 1e-5 if prec == "f" else 1e-12
+    gp.destroy()
+    hp.destroy()
+
+
 def test_error_contract_gpu(cuda):
     """reference test/cuda/cufinufft_error_handling.cu / test_makeplan.c / multigpu test."""
     import finufft_b200 as F
