@@ -230,6 +230,7 @@ def main():
     pts_h = synth_points(dim, M, rt, 1234 + rank, args.dist, nf[::-1])
     pts = [torch.from_numpy(p).to(dev) for p in pts_h]
     plan.enable_profiling(True)
+    plan.setpts(*pts)  # untimed: first-call module loading, pool growth
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     plan.setpts(*pts)

@@ -74,11 +74,20 @@ Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr
   if (dim < 1 || dim > 3) throw Failure{ERR_DIM_NOTVALID};
   if (ntr < 1) throw Failure{ERR_NTRANS_NOTVALID};
   DeviceGuard guard(opts.device);
+  {  // setpts scratch comes from the stream-ordered pool: keep freed blocks cached across calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, opts.device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   tol   = tol_;
   sigma = opts.upsampfac == 0.0 ? 2.0 : opts.upsampfac;
   batch = opts.maxbatch > 0 ? std::min(opts.maxbatch, ntr) : std::min(ntr, 8);
   if (opts.maxsub < 32) opts.maxsub = 32;
-  if (const char *env = getenv("B200_NUFFT_SWEEP")) opts.sweep = atoi(env);  // debugging aid
+  if (const char *env = getenv("B200_NUFFT_SWEEP")) opts.sweep = atoi(env);  // debugging aids
+  if (const char *env = getenv("B200_NUFFT_SORT")) opts.sort_radix = atoi(env) == 2;
   plan_kernel();
   if (type != 3) {
     for (int d = 0; d < dim; ++d) ms[d] = nmodes[d];
@@ -199,6 +208,28 @@ template<class T> void Engine<T>::plan_grid() {
 }
 
 // ------------------------------------------------------------------ setpts
+// scratch that lives for one setpts call, from the stream-ordered pool (no device-wide syncs)
+template<class U> struct Scratch {
+  U *p            = nullptr;
+  cudaStream_t st = nullptr;
+  Scratch(size_t n, cudaStream_t s) : st(s) {
+    if (n) CU(cudaMallocAsync((void **)&p, n * sizeof(U), s));
+  }
+  ~Scratch() {
+    if (p) cudaFreeAsync(p, st);
+  }
+  Scratch(const Scratch &)            = delete;
+  Scratch &operator=(const Scratch &) = delete;
+};
+
+static void refine_impl(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
+                        uint32_t *sidx, const uint32_t *binstart, const GridGeom<float> &g,
+                        cudaStream_t st) {
+  launch_refine_bins3(ns, packed, xs, ys, zs, sidx, binstart, g, st);
+}
+static void refine_impl(int, const Packed4<double> *, double *, double *, double *, uint32_t *,
+                        const uint32_t *, const GridGeom<double> &, cudaStream_t) {}
+
 template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z) {
   cudaStream_t st = opts.stream;
   const uint32_t m = (uint32_t)M;
@@ -207,34 +238,54 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
   if (dim > 2) zs_.alloc(M);
   sidx_.alloc(M);
   binstart_.alloc((size_t)geom.nbins + 1);
-  DevBuf<uint32_t> keys_a, keys_b, vals_b, hist, scan_tmp, nsubs, substart;
-  keys_a.alloc(M);
-  keys_b.alloc(M);
-  vals_b.alloc(M);
-  hist.alloc(256 * (size_t)kRadixMaxBlocks + 1);
   const size_t scan_n = std::max<size_t>(geom.nbins + 1, 256 * (size_t)kRadixMaxBlocks + 1);
-  scan_tmp.alloc(scan_n / 4096 + 8);
-
-  launch_bin_keys<T>(dim, x, y, z, m, geom, keys_a.p, st);
-  int nbits = 0;
-  while ((1ull << nbits) < (uint64_t)geom.nbins) ++nbits;
-  const int which = radix_sort_pairs(keys_a.p, keys_b.p, sidx_.p, vals_b.p, m, nbits, hist.p,
-                                     scan_tmp.p, st);
-  const uint32_t *sorted_keys = which ? keys_b.p : keys_a.p;
-  if (which && M) {  // result landed in the scratch value buffer
-    CU(cudaMemcpyAsync(sidx_.p, vals_b.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToDevice, st));
-  }
-  launch_bin_bounds(sorted_keys, m, geom.nbins, binstart_.p, st);
-  launch_gather_coords<T>(dim, x, y, z, sidx_.p, m, xs_.p, ys_.p, zs_.p, st);
-
-  // 3D float with a supported width: refine the order inside the bins for the sweep kernels
+  Scratch<uint32_t> scan_tmp(scan_n / 4096 + 8, st);
+  // 3D float with a supported width: the sweep kernels want the order inside the bins refined
   swept_ = std::is_same<T, float>::value && dim == 3 && sweep3_supported(ns) && opts.sweep &&
            nf[0] % 2 == 0 && M > 0;
-  if (swept_) refine_for_sweep(scan_tmp.p);
+  radix_order_ = opts.sort_radix != 0;
 
-  // subproblem list: every bin in chunks of at most maxsub points
-  nsubs.alloc(geom.nbins);
-  substart.alloc((size_t)geom.nbins + 1);
+  if (!radix_order_) {
+    // counting sort: bin counts (warp-aggregated atomics) -> scan -> placement -> gather
+    Scratch<uint32_t> keys(M, st), ranks(M, st), cnt(geom.nbins, st);
+    Scratch<Packed4<T>> packed(M, st);
+    CU(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * geom.nbins, st));
+    launch_bin_count<T>(dim, x, y, z, m, geom, keys.p, ranks.p, cnt.p, packed.p, st);
+    exclusive_scan_u32(cnt.p, binstart_.p, geom.nbins, scan_tmp.p, st);
+    launch_bin_place(keys.p, ranks.p, binstart_.p, m, sidx_.p, st);
+    if (swept_)
+      refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, st);
+    else
+      launch_gather_packed<T>(dim, packed.p, sidx_.p, m, xs_.p, ys_.p, zs_.p, st);
+    CU(cudaGetLastError());
+  } else {
+    // stable LSD radix sort of (bin key, index): yields the reference permutation directly
+    Scratch<uint32_t> keys_a(M, st), keys_b(M, st), vals_b(M, st);
+    Scratch<uint32_t> hist(256 * (size_t)kRadixMaxBlocks + 1, st);
+    launch_bin_keys<T>(dim, x, y, z, m, geom, keys_a.p, st);
+    int nbits = 0;
+    while ((1ull << nbits) < (uint64_t)geom.nbins) ++nbits;
+    const int which = radix_sort_pairs(keys_a.p, keys_b.p, sidx_.p, vals_b.p, m, nbits, hist.p,
+                                       scan_tmp.p, st);
+    const uint32_t *sorted_keys = which ? keys_b.p : keys_a.p;
+    if (which && M)  // result landed in the scratch value buffer
+      CU(cudaMemcpyAsync(sidx_.p, vals_b.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToDevice, st));
+    launch_bin_bounds(sorted_keys, m, geom.nbins, binstart_.p, st);
+    if (swept_) {
+      Scratch<Packed4<T>> packed(M, st);
+      Scratch<uint32_t> keys(M, st), ranks(M, st), cnt(geom.nbins, st);  // packs the coordinates
+      CU(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * geom.nbins, st));
+      launch_bin_count<T>(dim, x, y, z, m, geom, keys.p, ranks.p, cnt.p, packed.p, st);
+      refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, st);
+    } else
+      launch_gather_coords<T>(dim, x, y, z, sidx_.p, m, xs_.p, ys_.p, zs_.p, st);
+    CU(cudaGetLastError());
+  }
+
+  if (swept_) build_sweep_items(scan_tmp.p);
+
+  // subproblem list of the generic kernels: every bin in chunks of at most maxsub points
+  Scratch<uint32_t> nsubs(geom.nbins, st), substart((size_t)geom.nbins + 1, st);
   launch_sub_count(binstart_.p, geom.nbins, (uint32_t)opts.maxsub, nsubs.p, st);
   exclusive_scan_u32(nsubs.p, substart.p, geom.nbins, scan_tmp.p, st);
   uint32_t total = 0;
@@ -248,22 +299,13 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
     launch_sub_fill(binstart_.p, substart.p, geom.nbins, (uint32_t)opts.maxsub, sub_bin_.p,
                     sub_off_.p, st);
   CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(st));  // scratch buffers are freed on return
+  CU(cudaStreamSynchronize(st));
 }
 
-static void refine_impl(int ns, float *xs, float *ys, float *zs, uint32_t *sidx,
-                        const uint32_t *binstart, const GridGeom<float> &g, cudaStream_t st) {
-  launch_refine_bins3(ns, xs, ys, zs, sidx, binstart, g, st);
-}
-static void refine_impl(int, double *, double *, double *, uint32_t *, const uint32_t *,
-                        const GridGeom<double> &, cudaStream_t) {}
-template<class T> void Engine<T>::refine_for_sweep(uint32_t *scan_tmp) {
+template<class T> void Engine<T>::build_sweep_items(uint32_t *scan_tmp) {
   cudaStream_t st = opts.stream;
-  refine_impl(ns, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, st);
   const uint32_t nrows = (uint32_t)geom.nb[1] * (uint32_t)geom.nb[2];
-  DevBuf<uint32_t> nit, itstart;
-  nit.alloc(nrows);
-  itstart.alloc((size_t)nrows + 1);
+  Scratch<uint32_t> nit(nrows, st), itstart((size_t)nrows + 1, st);
   launch_row_item_count(binstart_.p, nrows, (uint32_t)geom.nb[0], kSweepItemPoints, nit.p, st);
   exclusive_scan_u32(nit.p, itstart.p, nrows, scan_tmp, st);
   uint32_t total = 0;
@@ -274,7 +316,6 @@ template<class T> void Engine<T>::refine_for_sweep(uint32_t *scan_tmp) {
   if (total)
     launch_row_item_fill(binstart_.p, itstart.p, nrows, (uint32_t)geom.nb[0], kSweepItemPoints,
                          items_.p, st);
-  CU(cudaStreamSynchronize(st));  // nit / itstart are freed on return
 }
 
 template<class T>
@@ -442,8 +483,8 @@ template<class T> void Engine<T>::copy_sort_to_host(uint32_t *out) const {
   if (M == 0) return;
   cudaStreamSynchronize(opts.stream);
   cuda_check(cudaMemcpy(out, sidx_.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToHost), "copy sort");
-  if (swept_) {
-    // The sweep kernels re-order points inside each bin; the reference's stable counting sort
+  if (swept_ || !radix_order_) {
+    // The counting sort leaves a bin's points in arrival order and the sweep kernels re-order them; the reference's stable counting sort
     // leaves them in ascending index order (include/finufft/spread.hpp:559-581), which is
     // restored here for inspection.
     std::vector<uint32_t> bs((size_t)geom.nbins + 1);

@@ -34,6 +34,7 @@ struct EngineOpts {
   int maxsub           = 1024;  // most points one warp takes from one bin
   int debug            = 0;
   int allow_eps_too_small = 1;
+  int sort_radix       = 0;     // 1: stable radix sort (reference permutation on the device)
   int sweep            = 1;     // 3D float: tube-sweep kernels (0 = generic kernels)
   int check_sigma      = 0;     // host (finufft_*) entry points apply the CPU feasibility rule
 };
@@ -96,7 +97,7 @@ template<class T> class Engine {
   void sort_points(const T *x, const T *y, const T *z);
   bool use_sweep3(const void *grid) const;
   cudaError_t sweep_run(bool spread, C *c, C *fw);
-  void refine_for_sweep(uint32_t *scan_tmp);
+  void build_sweep_items(uint32_t *scan_tmp);
   void run_spread(const C *c, C *fw);
   void run_interp(C *c, const C *fw);
   void spread_path(C *c, C *fk, int fsign);
@@ -119,6 +120,7 @@ template<class T> class Engine {
   DevBuf<SweepItem> items_;  // 3D float sweep kernels: work items, refined bin order in use
   uint32_t nitems_ = 0;
   bool swept_      = false;
+  bool radix_order_ = false;  // sidx_ is the reference permutation as it stands
   // type 3
   DevBuf<T> xp_[3], sp_[3];
   DevBuf<C> prephase_, deconv_, cp_;

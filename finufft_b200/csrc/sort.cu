@@ -333,48 +333,149 @@ void launch_sub_fill(const uint32_t *binstart, const uint32_t *substart, uint32_
                                                    sub_off);
 }
 
+// ------------------------------------------------------------------------------ counting sort
+template<class T, int DIM>
+__device__ __forceinline__ uint32_t bin_key(T x, T y, T z, const GridGeom<T> &g) {
+  // 1/binsize are powers of two, so the product is exact; conversion truncates (X >= 0).
+  uint32_t key = (uint32_t)(int)mul_rn(fold_rescale<T>(x, g.nf_t[0]), (T)(1.0 / kBinX));
+  if (DIM > 1)
+    key += (uint32_t)g.nb[0] * (uint32_t)(int)mul_rn(fold_rescale<T>(y, g.nf_t[1]), (T)(1.0 / kBinY));
+  if (DIM > 2)
+    key += (uint32_t)g.nb[0] * (uint32_t)g.nb[1] *
+           (uint32_t)(int)mul_rn(fold_rescale<T>(z, g.nf_t[2]), (T)(1.0 / kBinZ));
+  return key < g.nbins ? key : g.nbins - 1;  // only non-finite input can trip this
+}
+
+template<class T, int DIM>
+__global__ void __launch_bounds__(256)
+k_bin_count(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z, uint32_t M,
+            GridGeom<T> g, uint32_t *__restrict__ keys, uint32_t *__restrict__ ranks,
+            uint32_t *__restrict__ cnt, Packed4<T> *__restrict__ packed) {
+  const int lane         = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t stride  = gridDim.x * blockDim.x;
+  for (uint32_t i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < M; i0 += stride) {
+    const uint32_t i = i0 + lane;
+    const bool valid = i < M;
+    T px = 0, py = 0, pz = 0;
+    if (valid) {
+      px = x[i];
+      if (DIM > 1) py = y[i];
+      if (DIM > 2) pz = z[i];
+    }
+    const uint32_t key = valid ? bin_key<T, DIM>(px, py, pz, g) : 0xffffffffu;
+    // one atomic per distinct bin in the warp
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    const int leader     = __ffs(peers) - 1;
+    uint32_t base        = 0;
+    if (valid && lane == leader) base = atomicAdd(&cnt[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (valid) {
+      keys[i]   = key;
+      ranks[i]  = base + __popc(peers & lt_mask);
+      packed[i] = Packed4<T>{px, py, pz, (T)0};
+    }
+  }
+}
+template<class T>
+void launch_bin_count(int dim, const T *x, const T *y, const T *z, uint32_t M,
+                      const GridGeom<T> &g, uint32_t *keys, uint32_t *ranks, uint32_t *cnt,
+                      Packed4<T> *packed, cudaStream_t st) {
+  if (M == 0) return;
+  const int nb = grid_for(M, 256, 16);
+  if (dim == 1) k_bin_count<T, 1><<<nb, 256, 0, st>>>(x, y, z, M, g, keys, ranks, cnt, packed);
+  else if (dim == 2) k_bin_count<T, 2><<<nb, 256, 0, st>>>(x, y, z, M, g, keys, ranks, cnt, packed);
+  else k_bin_count<T, 3><<<nb, 256, 0, st>>>(x, y, z, M, g, keys, ranks, cnt, packed);
+}
+template void launch_bin_count<float>(int, const float *, const float *, const float *, uint32_t,
+                                      const GridGeom<float> &, uint32_t *, uint32_t *, uint32_t *,
+                                      Packed4<float> *, cudaStream_t);
+template void launch_bin_count<double>(int, const double *, const double *, const double *,
+                                       uint32_t, const GridGeom<double> &, uint32_t *, uint32_t *,
+                                       uint32_t *, Packed4<double> *, cudaStream_t);
+
+__global__ void k_bin_place(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ ranks,
+                            const uint32_t *__restrict__ binstart, uint32_t M,
+                            uint32_t *__restrict__ sidx) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride)
+    sidx[binstart[keys[i]] + ranks[i]] = i;
+}
+void launch_bin_place(const uint32_t *keys, const uint32_t *ranks, const uint32_t *binstart,
+                      uint32_t M, uint32_t *sidx, cudaStream_t st) {
+  if (M) k_bin_place<<<grid_for(M, 256, 16), 256, 0, st>>>(keys, ranks, binstart, M, sidx);
+}
+
+template<class T, int DIM>
+__global__ void k_gather_packed(const Packed4<T> *__restrict__ packed,
+                                const uint32_t *__restrict__ sidx, uint32_t M, T *__restrict__ xs,
+                                T *__restrict__ ys, T *__restrict__ zs) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
+    const Packed4<T> p = packed[sidx[i]];
+    xs[i] = p.x;
+    if (DIM > 1) ys[i] = p.y;
+    if (DIM > 2) zs[i] = p.z;
+  }
+}
+template<class T>
+void launch_gather_packed(int dim, const Packed4<T> *packed, const uint32_t *sidx, uint32_t M,
+                          T *xs, T *ys, T *zs, cudaStream_t st) {
+  if (M == 0) return;
+  const int nb = grid_for(M, 256, 16);
+  if (dim == 1) k_gather_packed<T, 1><<<nb, 256, 0, st>>>(packed, sidx, M, xs, ys, zs);
+  else if (dim == 2) k_gather_packed<T, 2><<<nb, 256, 0, st>>>(packed, sidx, M, xs, ys, zs);
+  else k_gather_packed<T, 3><<<nb, 256, 0, st>>>(packed, sidx, M, xs, ys, zs);
+}
+template void launch_gather_packed<float>(int, const Packed4<float> *, const uint32_t *, uint32_t,
+                                          float *, float *, float *, cudaStream_t);
+template void launch_gather_packed<double>(int, const Packed4<double> *, const uint32_t *,
+                                           uint32_t, double *, double *, double *, cudaStream_t);
+
 // ------------------------------------------------------------------------------ sweep support
-// One warp per bin.  The bin's points (coordinates + index) are pulled into shared memory in
-// batches, ranked by a stable counting sort on key = g*5 + jb (g: x window position inside the
-// bin in steps of two cells, jb: y stencil start inside the bin) and written back in place.
+// One warp per bin.  The bin's points (index + packed coordinates) are pulled into shared
+// memory in batches, bucketed by key = g*5 + jb (g: x window position inside the bin in steps
+// of two cells, jb: y stencil start inside the bin), ordered by index inside each bucket and
+// written out: coordinates to the sorted arrays, indices back to sidx.
 constexpr int kRefCap = 512, kRefWarps = 4, kRefKeys = 64;
 
 template<int NS>
 __global__ void __launch_bounds__(kRefWarps * 32)
-k_refine_bins3(float *__restrict__ xs, float *__restrict__ ys, float *__restrict__ zs,
-               uint32_t *__restrict__ sidx, const uint32_t *__restrict__ binstart,
-               GridGeom<float> g) {
+k_refine_bins3(const Packed4<float> *__restrict__ packed, float *__restrict__ xs,
+               float *__restrict__ ys, float *__restrict__ zs, uint32_t *__restrict__ sidx,
+               const uint32_t *__restrict__ binstart, GridGeom<float> g) {
   __shared__ float sx[kRefWarps][kRefCap], sy[kRefWarps][kRefCap], sz[kRefWarps][kRefCap];
   __shared__ uint32_t si[kRefWarps][kRefCap];
-  __shared__ uint16_t spos[kRefWarps][kRefCap];
-  __shared__ int cnt[kRefWarps][kRefKeys];
+  __shared__ uint16_t skey[kRefWarps][kRefCap], sord[kRefWarps][kRefCap];
+  __shared__ int cnt[kRefWarps][kRefKeys + 1], fill[kRefWarps][kRefKeys];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t nwarps = gridDim.x * kRefWarps;
   constexpr int HL = NS / 2, XB = 4, NG = kBinX / 2 + 1, NJB = kBinY + 1;
   for (uint32_t bin = blockIdx.x * kRefWarps + warp; bin < g.nbins; bin += nwarps) {
     const uint32_t qs = binstart[bin], qe = binstart[bin + 1];
-    if (qe - qs < 2) continue;
+    if (qe == qs) continue;
     const int i1 = bin % g.nb[0], i2 = (bin / g.nb[0]) % g.nb[1];
     for (uint32_t q0 = qs; q0 < qe; q0 += kRefCap) {
       const int n = (int)min((uint32_t)kRefCap, qe - q0);
       cnt[warp][lane] = 0, cnt[warp][lane + 32] = 0;
+      fill[warp][lane] = 0, fill[warp][lane + 32] = 0;
       __syncwarp();
       for (int k = lane; k < n; k += 32) {
-        const float x = xs[q0 + k], y = ys[q0 + k];
-        sx[warp][k] = x, sy[warp][k] = y, sz[warp][k] = zs[q0 + k], si[warp][k] = sidx[q0 + k];
+        const uint32_t j        = sidx[q0 + k];
+        const Packed4<float> pt = packed[j];
+        sx[warp][k] = pt.x, sy[warp][k] = pt.y, sz[warp][k] = pt.z, si[warp][k] = j;
         int i0, j0;
         float t;
-        stencil_start<float, NS>(fold_rescale<float>(x, g.nf_t[0]), i0, t);
-        stencil_start<float, NS>(fold_rescale<float>(y, g.nf_t[1]), j0, t);
+        stencil_start<float, NS>(fold_rescale<float>(pt.x, g.nf_t[0]), i0, t);
+        stencil_start<float, NS>(fold_rescale<float>(pt.y, g.nf_t[1]), j0, t);
         const int gg  = min(max((i0 - (kBinX * i1 - XB)) >> 1, 0), NG - 1);
         const int jb  = min(max(j0 - (kBinY * i2 - HL), 0), kBinY);
         const int key = gg * NJB + jb;
-        spos[warp][k] = (uint16_t)key;
+        skey[warp][k] = (uint16_t)key;
         atomicAdd(&cnt[warp][key], 1);
       }
       __syncwarp();
-      {  // exclusive scan of the 64 counters, two per lane
+      {  // exclusive scan of the 64 counters, two per lane; cnt[64] = n
         const int v0 = cnt[warp][2 * lane], v1 = cnt[warp][2 * lane + 1];
         int incl = v0 + v1;
 #pragma unroll
@@ -385,37 +486,39 @@ k_refine_bins3(float *__restrict__ xs, float *__restrict__ ys, float *__restrict
         __syncwarp();
         cnt[warp][2 * lane]     = incl - v0 - v1;
         cnt[warp][2 * lane + 1] = incl - v1;
+        if (lane == 31) cnt[warp][kRefKeys] = incl;
       }
       __syncwarp();
-      // stable ranks: rounds of 32 points in order, lanes in order inside a round
-      for (int k0 = 0; k0 < n; k0 += 32) {
-        const int k       = k0 + lane;
-        const bool valid  = k < n;
-        const int key     = valid ? (int)spos[warp][k] : kRefKeys + lane;  // invalid: unique
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-        const int leader  = __ffs(peers) - 1;
-        int base          = 0;
-        if (valid && lane == leader) base = cnt[warp][key];
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (valid) spos[warp][k] = (uint16_t)(base + __popc(peers & lt_mask));
-        if (valid && lane == leader) cnt[warp][key] = base + __popc(peers);
-        __syncwarp();
-      }
+      // bucket the elements (any order inside a bucket) ...
       for (int k = lane; k < n; k += 32) {
-        const uint32_t dst = q0 + spos[warp][k];
-        xs[dst] = sx[warp][k], ys[dst] = sy[warp][k], zs[dst] = sz[warp][k], sidx[dst] = si[warp][k];
+        const int key = skey[warp][k];
+        sord[warp][cnt[warp][key] + atomicAdd(&fill[warp][key], 1)] = (uint16_t)k;
+      }
+      __syncwarp();
+      // ... then rank every element inside its bucket by index and write it out
+      for (int p = lane; p < n; p += 32) {
+        const int k = sord[warp][p], key = skey[warp][k];
+        const uint32_t mine = si[warp][k];
+        const int b0 = cnt[warp][key], b1 = cnt[warp][key + 1];
+        int r = 0;
+        for (int q = b0; q < b1; ++q) r += si[warp][sord[warp][q]] < mine ? 1 : 0;
+        const uint32_t dst = q0 + b0 + r;
+        xs[dst] = sx[warp][k], ys[dst] = sy[warp][k], zs[dst] = sz[warp][k], sidx[dst] = mine;
       }
       __syncwarp();
     }
   }
 }
 
-void launch_refine_bins3(int ns, float *xs, float *ys, float *zs, uint32_t *sidx,
-                         const uint32_t *binstart, const GridGeom<float> &g, cudaStream_t st) {
+void launch_refine_bins3(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
+                         uint32_t *sidx, const uint32_t *binstart, const GridGeom<float> &g,
+                         cudaStream_t st) {
   const int nb = grid_for((g.nbins + kRefWarps - 1) / kRefWarps * 32 * kRefWarps, kRefWarps * 32, 16);
   switch (ns) {
-#define B200_REF(NSV) \
-  case NSV: k_refine_bins3<NSV><<<nb, kRefWarps * 32, 0, st>>>(xs, ys, zs, sidx, binstart, g); break;
+#define B200_REF(NSV)                                                                       \
+  case NSV:                                                                                 \
+    k_refine_bins3<NSV><<<nb, kRefWarps * 32, 0, st>>>(packed, xs, ys, zs, sidx, binstart, g); \
+    break;
     B200_REF(2) B200_REF(3) B200_REF(4) B200_REF(5) B200_REF(6) B200_REF(7)
 #undef B200_REF
   default: break;

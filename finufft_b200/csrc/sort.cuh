@@ -55,13 +55,36 @@ void launch_sub_fill(const uint32_t *binstart, const uint32_t *substart, uint32_
 
 void launch_iota(uint32_t *v, uint32_t n, cudaStream_t st);
 
+// --- counting sort by bin (the default setpts path) ----------------------------------------
+// Bin counting with warp-aggregated atomics, prefix scan of the counts, placement of every
+// index in its bin.  The order inside a bin is the order the atomics happened to return; the
+// bins and their ranges are exactly the reference's, and sorting each bin's indices ascending
+// gives the reference's stable permutation (include/finufft/spread.hpp:559-581).
+template<class T> struct alignas(sizeof(T) * 4) Packed4 {
+  T x, y, z, w;
+};
+// keys[i] = bin of point i, ranks[i] = its arrival number inside the bin, cnt[bin] += 1,
+// packed[i] = (x,y,z,0).  cnt must be zero on entry.
+template<class T>
+void launch_bin_count(int dim, const T *x, const T *y, const T *z, uint32_t M,
+                      const GridGeom<T> &g, uint32_t *keys, uint32_t *ranks, uint32_t *cnt,
+                      Packed4<T> *packed, cudaStream_t st);
+// sidx[binstart[keys[i]] + ranks[i]] = i
+void launch_bin_place(const uint32_t *keys, const uint32_t *ranks, const uint32_t *binstart,
+                      uint32_t M, uint32_t *sidx, cudaStream_t st);
+// coordinates into sorted order from the packed copy (one 16/32-byte read per point)
+template<class T>
+void launch_gather_packed(int dim, const Packed4<T> *packed, const uint32_t *sidx, uint32_t M,
+                          T *xs, T *ys, T *zs, cudaStream_t st);
+
 // --- 3D sweep support (sweep3d.cuh) --------------------------------------------------------
-// Re-orders the points inside every bin, in place, by (x window position, y stencil start) so
-// that a row of bins read front to back is sorted by x window position.  The order stays a
-// refinement of the bin order: bins keep their ranges.  Stable (ties keep the bin order).
-// ns = kernel width (fixes the stencil start rule ceil(X - ns/2)).
-void launch_refine_bins3(int ns, float *xs, float *ys, float *zs, uint32_t *sidx,
-                         const uint32_t *binstart, const GridGeom<float> &g, cudaStream_t st);
+// Orders the points inside every bin by (x window position, y stencil start, index), so that a
+// row of bins read front to back is sorted by x window position, and gathers their coordinates.
+// The order stays a refinement of the bin order: bins keep their ranges.  Deterministic.
+// ns = kernel width (fixes the stencil start rule ceil(X - ns/2)).  sidx is updated in place.
+void launch_refine_bins3(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
+                         uint32_t *sidx, const uint32_t *binstart, const GridGeom<float> &g,
+                         cudaStream_t st);
 
 // Work items of the sweep kernels: every row of bins (i2, i3) cut into runs of at most
 // `maxpts` consecutive points.  item = {row, first point, one past last point}.

@@ -49,6 +49,22 @@ def test_sort_permutation_bit_exact(cuda, oracle, prec, dim, modes, kind):
     assert np.array_equal(gp.sort_permutation().astype(np.int64), op.perm())
 
 
+@pytest.mark.parametrize("dim,modes", [(2, (70, 52)), (3, (24, 30, 20))])
+def test_radix_sort_is_reference_permutation_on_device(cuda, oracle, dim, modes, monkeypatch):
+    """B200_NUFFT_SORT=2 selects the stable LSD radix sort, whose raw device output (no per-bin
+    restoring on the host) must already be the reference CPU permutation."""
+    import finufft_b200 as F
+    monkeypatch.setenv("B200_NUFFT_SORT", "2")
+    monkeypatch.setenv("B200_NUFFT_SWEEP", "0")
+    rng = np.random.default_rng(13)
+    gp, op = _plans(F, oracle, 1, modes, 1, 1e-6, "f")
+    for kind in ("uniform", "cluster"):
+        pts = make_points(rng, dim, 50_000, np.float32, kind, nf=gp.info()["nf"][::-1])[:dim]
+        gp.setpts(*[cuda.from_numpy(p).cuda() for p in pts])
+        op.setpts(*(pts[::-1] + [None] * (3 - dim)))
+        assert np.array_equal(gp.sort_permutation().astype(np.int64), op.perm())
+
+
 def test_sort_ragged_sizes(cuda, oracle):
     """M = 0, 1, 31, 33, 2047, 2049 ... (tile edges of the radix sort) and one-bin grids."""
     import finufft_b200 as F
