@@ -155,6 +155,47 @@ def cpu_run(type_, modes, M, tol, dtype, steps, warmup, dist):
     return float(np.mean(times)), t_setpts, nthr
 
 
+# --------------------------------------------------------------------------------- z-slab leg
+def zslab_leg(type_, modes, M, tol, rank, world, dev, steps, warmup, barrier):
+    """Strong scaling of ONE transform of M points over `world` GPUs: z-slab decomposition of the
+    fine grid (finufft_b200/zslab.py: ghost-plane send/recv + slab->pencil all_to_all over NCCL).
+    Points are generated already partitioned by slab; outputs stay sharded."""
+    import torch
+    import torch.distributed as dist_
+    from finufft_b200.zslab import SlabPlan
+    try:
+        sp = SlabPlan(type_, modes, tol, 1 if type_ == 1 else -1, "complex64")
+    except ValueError as exc:
+        return {"unavailable": str(exc)}
+    Ml = M // world
+    g = torch.Generator(device=dev)
+    g.manual_seed(500 + rank)
+    h = 2 * np.pi / sp.nf[0]
+    top = float(np.nextafter(np.float32(-np.pi + h * sp.z1), np.float32(-4)))
+    z = (-np.pi + h * (sp.z0 + sp.nz * torch.rand(Ml, device=dev, generator=g))).float().clamp_(max=top)
+    y = ((torch.rand(Ml, device=dev, generator=g) * 2 - 1) * np.pi).float()
+    x = ((torch.rand(Ml, device=dev, generator=g) * 2 - 1) * np.pi).float()
+    sp.setpts(z, y, x)
+    shape = (Ml,) if type_ == 1 else (modes[0], sp.y_hi - sp.y_lo, modes[2])
+    data = torch.view_as_complex(torch.randn(shape + (2,), device=dev, generator=g))
+    for _ in range(max(warmup, 3)):
+        sp.execute(data)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sp.execute(data)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dist_.all_reduce(t, op=dist_.ReduceOp.MAX)
+    sp.destroy()
+    ms = float(t.item())
+    return {"value": M / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "scaling": "strong",
+            "workload": f"one transform, M={M:.3g} total points pre-partitioned by z-slab over "
+                        f"{world} GPUs, outputs left sharded"}
+
+
 # --------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -168,6 +209,8 @@ def main():
     ap.add_argument("--cpu-sample", type=float, default=None,
                     help="points in the CPU sample (default: sized for ~10-30 s)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-zslab", action="store_true",
+                    help="N>1: skip the extra strong-scaling (z-slab sharded single transform) leg")
     args = ap.parse_args()
 
     type_, modes, M, tol, dtype, ntr = WORKLOADS[args.workload]
@@ -310,6 +353,10 @@ def main():
     cbytes = 8 if rbytes == 4 else 16
     hplan.destroy()
 
+    zslab = None
+    if world > 1 and dim == 3 and dtype == "complex64" and ntr == 1 and not args.no_zslab:
+        zslab = zslab_leg(type_, modes, M, tol, rank, world, dev, args.steps, args.warmup, barrier)
+
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
         abytes = algorithmic_bytes(dim, M, nf, rbytes)
@@ -344,6 +391,8 @@ def main():
                 "stages_ms": stage_avg, "setpts_ms": setpts_ms, "setpts_wall_ms": setpts_wall_ms,
                 "value_with_setpts": world * M * ntr / ((ms_per_step + setpts_ms) * 1e-3),
                 "plan": {"ns": info["ns"], "nf": nf, "nsub": info["nsub"]}}
+        if zslab is not None:
+            line["zslab"] = zslab
         print(json.dumps(line), flush=True)
     plan.destroy()
     if world > 1:
