@@ -63,6 +63,16 @@ def measured_hbm_peak():
     return 6650.0, "fallback"
 
 
+def ncu_traffic(workload, dist):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_summary.py); None if no capture is recorded."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(f"{workload}:{dist}", {}).get("dram_bytes")
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -78,7 +88,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -200,7 +210,7 @@ def zslab_leg(type_, modes, M, tol, rank, world, dev, steps, warmup, barrier):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3_t1", choices=sorted(WORKLOADS))
@@ -361,11 +371,22 @@ def main():
         peak, peak_kind = measured_hbm_peak()
         abytes = algorithmic_bytes(dim, M, nf, rbytes)
         kernel_ms = stage_avg["spreadinterp"] / ntr  # one launch per transform
+        swept = dim == 3 and rbytes == 4 and info["ns"] in (6, 7)
+        kernel_name = (f"k_sweep3<{info['ns']},{'true' if type_ == 1 else 'false'}>" if swept
+                       else ("k_spread" if type_ == 1 else "k_interp"))
         achieved = abytes / (kernel_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_spread" if type_ == 1 else "k_interp",
+        roofline = {"bound": "hbm", "kernel": kernel_name,
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_kind, "algorithmic_bytes": abytes,
-                    "kernel_ms": kernel_ms}
+                    "traffic": ncu_traffic(args.workload, args.dist), "peak_source": peak_kind,
+                    "algorithmic_bytes": abytes, "kernel_ms": kernel_ms}
+        # secondary roof (SURVEY.md 8(d) "which roof binds"): ns^d complex cell updates per
+        # point against the packed-FFMA2 rate measured on this part (tools/micro/micro1.cu,
+        # profiles/r1_micro_ffma2_red.txt: 17.6e12 cell updates/s)
+        if rbytes == 4:
+            cells = float(info["ns"]) ** dim * M
+            roofline["fp32"] = {"achieved_tcell_s": cells / (kernel_ms * 1e-3) / 1e12,
+                                "peak_tcell_s": 17.6, "frac": cells / (kernel_ms * 1e-3) / 17.6e12,
+                                "floor_ms": cells / 17.6e12 * 1e3}
         cpu = None
         if not args.no_cpu:
             cpu_M = int(args.cpu_sample or min(M, 10_000_000))

@@ -222,13 +222,23 @@ template<class U> struct Scratch {
   Scratch &operator=(const Scratch &) = delete;
 };
 
+// refined order inside the bins for the sweep kernels; work units = 512-point chunks of bins
 static void refine_impl(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
                         uint32_t *sidx, const uint32_t *binstart, const GridGeom<float> &g,
-                        cudaStream_t st) {
-  launch_refine_bins3(ns, packed, xs, ys, zs, sidx, binstart, g, st);
+                        uint64_t M, uint32_t *scan_tmp, cudaStream_t st) {
+  const uint32_t max_chunks =
+      (uint32_t)(M / kRefineChunk + std::min<uint64_t>(g.nbins, M));
+  Scratch<uint32_t> nch(g.nbins, st), chstart((size_t)g.nbins + 1, st);
+  Scratch<uint32_t> chunk_bin(max_chunks, st), chunk_off(max_chunks, st);
+  launch_sub_count(binstart, g.nbins, kRefineChunk, nch.p, st);
+  exclusive_scan_u32(nch.p, chstart.p, g.nbins, scan_tmp, st);
+  launch_sub_fill(binstart, chstart.p, g.nbins, kRefineChunk, chunk_bin.p, chunk_off.p, st);
+  launch_refine_bins3(ns, packed, xs, ys, zs, sidx, binstart, chunk_bin.p, chunk_off.p,
+                      chstart.p + g.nbins, max_chunks, g, st);
 }
 static void refine_impl(int, const Packed4<double> *, double *, double *, double *, uint32_t *,
-                        const uint32_t *, const GridGeom<double> &, cudaStream_t) {}
+                        const uint32_t *, const GridGeom<double> &, uint64_t, uint32_t *,
+                        cudaStream_t) {}
 
 template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z) {
   cudaStream_t st = opts.stream;
@@ -254,7 +264,8 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
     exclusive_scan_u32(cnt.p, binstart_.p, geom.nbins, scan_tmp.p, st);
     launch_bin_place(keys.p, ranks.p, binstart_.p, m, sidx_.p, st);
     if (swept_)
-      refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, st);
+      refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
+                  scan_tmp.p, st);
     else
       launch_gather_packed<T>(dim, packed.p, sidx_.p, m, xs_.p, ys_.p, zs_.p, st);
     CU(cudaGetLastError());
@@ -276,7 +287,8 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
       Scratch<uint32_t> keys(M, st), ranks(M, st), cnt(geom.nbins, st);  // packs the coordinates
       CU(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * geom.nbins, st));
       launch_bin_count<T>(dim, x, y, z, m, geom, keys.p, ranks.p, cnt.p, packed.p, st);
-      refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, st);
+      refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
+                  scan_tmp.p, st);
     } else
       launch_gather_coords<T>(dim, x, y, z, sidx_.p, m, xs_.p, ys_.p, zs_.p, st);
     CU(cudaGetLastError());
@@ -469,8 +481,7 @@ template<class T> void Engine<T>::interp_path(C *c, C *fk, int fsign) {
 template<class T> void Engine<T>::execute(C *c, C *fk, bool adjoint) {
   DeviceGuard guard(opts.device);
   if (type == 3) {
-    if (adjoint) throw Failure{ERR_TYPE_NOTVALID};
-    exec_type3(c, fk);
+    exec_type3(c, fk, adjoint);
     return;
   }
   const bool spreading = (type == 1) != adjoint;

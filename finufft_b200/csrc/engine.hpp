@@ -102,7 +102,7 @@ template<class T> class Engine {
   void run_interp(C *c, const C *fw);
   void spread_path(C *c, C *fk, int fsign);
   void interp_path(C *c, C *fk, int fsign);
-  void exec_type3(C *c, C *fk);
+  void exec_type3(C *c, C *fk, bool adjoint);
   void setpts_type3(int64_t M, const T *x, const T *y, const T *z, int64_t N, const T *s,
                     const T *t, const T *u);
 
@@ -123,7 +123,7 @@ template<class T> class Engine {
   bool radix_order_ = false;  // sidx_ is the reference permutation as it stands
   // type 3
   DevBuf<T> xp_[3], sp_[3];
-  DevBuf<C> prephase_, deconv_, cp_;
+  DevBuf<C> prephase_, deconv_, cp_, ck_;
   std::unique_ptr<Engine<T>> inner_;
   T t3C_[3] = {0, 0, 0}, t3D_[3] = {0, 0, 0}, t3h_[3] = {0, 0, 0}, t3gam_[3] = {1, 1, 1};
 };

@@ -438,12 +438,15 @@ template void launch_gather_packed<double>(int, const Packed4<double> *, const u
 // of two cells, jb: y stencil start inside the bin), ordered by index inside each bucket and
 // written out: coordinates to the sorted arrays, indices back to sidx.
 constexpr int kRefCap = 512, kRefWarps = 4, kRefKeys = 64;
+static_assert(kRefCap == (int)kRefineChunk, "chunk size");
 
 template<int NS>
 __global__ void __launch_bounds__(kRefWarps * 32)
 k_refine_bins3(const Packed4<float> *__restrict__ packed, float *__restrict__ xs,
                float *__restrict__ ys, float *__restrict__ zs, uint32_t *__restrict__ sidx,
-               const uint32_t *__restrict__ binstart, GridGeom<float> g) {
+               const uint32_t *__restrict__ binstart, const uint32_t *__restrict__ chunk_bin,
+               const uint32_t *__restrict__ chunk_off, const uint32_t *__restrict__ nchunks,
+               GridGeom<float> g) {
   __shared__ float sx[kRefWarps][kRefCap], sy[kRefWarps][kRefCap], sz[kRefWarps][kRefCap];
   __shared__ uint32_t si[kRefWarps][kRefCap];
   __shared__ uint16_t skey[kRefWarps][kRefCap], sord[kRefWarps][kRefCap];
@@ -451,12 +454,12 @@ k_refine_bins3(const Packed4<float> *__restrict__ packed, float *__restrict__ xs
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t nwarps = gridDim.x * kRefWarps;
   constexpr int HL = NS / 2, XB = 4, NG = kBinX / 2 + 1, NJB = kBinY + 1;
-  for (uint32_t bin = blockIdx.x * kRefWarps + warp; bin < g.nbins; bin += nwarps) {
-    const uint32_t qs = binstart[bin], qe = binstart[bin + 1];
-    if (qe == qs) continue;
+  const uint32_t total = *nchunks;
+  for (uint32_t ch = blockIdx.x * kRefWarps + warp; ch < total; ch += nwarps) {
+    const uint32_t bin = chunk_bin[ch], q0 = chunk_off[ch];
     const int i1 = bin % g.nb[0], i2 = (bin / g.nb[0]) % g.nb[1];
-    for (uint32_t q0 = qs; q0 < qe; q0 += kRefCap) {
-      const int n = (int)min((uint32_t)kRefCap, qe - q0);
+    {
+      const int n = (int)min((uint32_t)kRefCap, binstart[bin + 1] - q0);
       cnt[warp][lane] = 0, cnt[warp][lane + 32] = 0;
       fill[warp][lane] = 0, fill[warp][lane + 32] = 0;
       __syncwarp();
@@ -511,13 +514,16 @@ k_refine_bins3(const Packed4<float> *__restrict__ packed, float *__restrict__ xs
 }
 
 void launch_refine_bins3(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
-                         uint32_t *sidx, const uint32_t *binstart, const GridGeom<float> &g,
-                         cudaStream_t st) {
-  const int nb = grid_for((g.nbins + kRefWarps - 1) / kRefWarps * 32 * kRefWarps, kRefWarps * 32, 16);
+                         uint32_t *sidx, const uint32_t *binstart, const uint32_t *chunk_bin,
+                         const uint32_t *chunk_off, const uint32_t *nchunks, uint32_t max_chunks,
+                         const GridGeom<float> &g, cudaStream_t st) {
+  if (max_chunks == 0) return;
+  const int nb = grid_for((max_chunks + kRefWarps - 1) / kRefWarps * 32 * kRefWarps, kRefWarps * 32, 16);
   switch (ns) {
-#define B200_REF(NSV)                                                                       \
-  case NSV:                                                                                 \
-    k_refine_bins3<NSV><<<nb, kRefWarps * 32, 0, st>>>(packed, xs, ys, zs, sidx, binstart, g); \
+#define B200_REF(NSV)                                                                          \
+  case NSV:                                                                                    \
+    k_refine_bins3<NSV><<<nb, kRefWarps * 32, 0, st>>>(packed, xs, ys, zs, sidx, binstart,     \
+                                                       chunk_bin, chunk_off, nchunks, g);      \
     break;
     B200_REF(2) B200_REF(3) B200_REF(4) B200_REF(5) B200_REF(6) B200_REF(7)
 #undef B200_REF

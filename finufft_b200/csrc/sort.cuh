@@ -82,9 +82,14 @@ void launch_gather_packed(int dim, const Packed4<T> *packed, const uint32_t *sid
 // row of bins read front to back is sorted by x window position, and gathers their coordinates.
 // The order stays a refinement of the bin order: bins keep their ranges.  Deterministic.
 // ns = kernel width (fixes the stencil start rule ceil(X - ns/2)).  sidx is updated in place.
+// Work units are chunks of at most kRefineChunk consecutive points of one bin, (chunk_bin,
+// chunk_off) with the count on the device, so a bin holding most of the points (clustered
+// input) is shared by many warps; the order is refined inside each chunk.
+constexpr uint32_t kRefineChunk = 512;
 void launch_refine_bins3(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
-                         uint32_t *sidx, const uint32_t *binstart, const GridGeom<float> &g,
-                         cudaStream_t st);
+                         uint32_t *sidx, const uint32_t *binstart, const uint32_t *chunk_bin,
+                         const uint32_t *chunk_off, const uint32_t *nchunks, uint32_t max_chunks,
+                         const GridGeom<float> &g, cudaStream_t st);
 
 // Work items of the sweep kernels: every row of bins (i2, i3) cut into runs of at most
 // `maxpts` consecutive points.  item = {row, first point, one past last point}.

@@ -9,6 +9,7 @@
 // deconvolution, run the inner type-2 plan whose "modes" are that grid, multiply).
 // The GPU reference does the same with thrust calls (src/cuda/setpts.cu:77-314,
 // src/cuda/execute.cu:208-258); here the element-wise steps are three small kernels.
+#include <algorithm>
 #include <cmath>
 #include <limits>
 
@@ -265,27 +266,46 @@ void Engine<T>::setpts_type3(int64_t M_, const T *x, const T *y, const T *z, int
   mark(5);
 }
 
-template<class T> void Engine<T>::exec_type3(C *c, C *fk) {
+template<class T> void Engine<T>::exec_type3(C *c, C *fk, bool adjoint) {
   if (!inner_) throw Failure{ERR_PLAN_NOTVALID};
   cudaStream_t st = opts.stream;
   const int64_t G = grid_cells();
+  if (adjoint) ck_.alloc((size_t)std::max<int64_t>(nk, 1));
   for (int b = 0; b < ntr; ++b) {
     C *cb  = c + (int64_t)b * M;
     C *fkb = fk + (int64_t)b * nk;
-    order_[0] = 0, order_[1] = 1, order_[2] = 2;
-    mark(0);
-    launch_cmul<T>(1, cb, prephase_.p, cp_.p, M, 0, st);
-    ++launches;
-    cu(cudaMemsetAsync(fw_.p, 0, sizeof(C) * (size_t)G, st));
-    run_spread(cp_.p, fw_.p);
-    mark(1);
-    const uint64_t before = inner_->launches;
-    inner_->execute(fkb, fw_.p, false);
-    launches += inner_->launches - before;
-    mark(2);
-    launch_cmul<T>(1, fkb, deconv_.p, fkb, nk, 0, st);
-    ++launches;
-    mark(3);
+    if (!adjoint) {
+      order_[0] = 0, order_[1] = 1, order_[2] = 2;
+      mark(0);
+      launch_cmul<T>(1, cb, prephase_.p, cp_.p, M, 0, st);
+      ++launches;
+      cu(cudaMemsetAsync(fw_.p, 0, sizeof(C) * (size_t)G, st));
+      run_spread(cp_.p, fw_.p);
+      mark(1);
+      const uint64_t before = inner_->launches;
+      inner_->execute(fkb, fw_.p, false);
+      launches += inner_->launches - before;
+      mark(2);
+      launch_cmul<T>(1, fkb, deconv_.p, fkb, nk, 0, st);
+      ++launches;
+      mark(3);
+    } else {
+      // adjoint (include/finufft/execute.hpp:515-545): conj deconvolve, adjoint of the inner
+      // type 2 (a type 1 from the targets onto the fw grid), interpolate, conj post-phase
+      order_[0] = 2, order_[1] = 1, order_[2] = 0;
+      mark(0);
+      launch_cmul<T>(1, fkb, deconv_.p, ck_.p, nk, 1, st);
+      ++launches;
+      mark(1);
+      const uint64_t before = inner_->launches;
+      inner_->execute(ck_.p, fw_.p, true);
+      launches += inner_->launches - before;
+      mark(2);
+      run_interp(cb, fw_.p);
+      launch_cmul<T>(1, cb, prephase_.p, cb, M, 1, st);
+      ++launches;
+      mark(3);
+    }
   }
   cu(cudaGetLastError());
 }
@@ -295,6 +315,6 @@ template void Engine<float>::setpts_type3(int64_t, const float *, const float *,
 template void Engine<double>::setpts_type3(int64_t, const double *, const double *,
                                            const double *, int64_t, const double *,
                                            const double *, const double *);
-template void Engine<float>::exec_type3(float2 *, float2 *);
-template void Engine<double>::exec_type3(double2 *, double2 *);
+template void Engine<float>::exec_type3(float2 *, float2 *, bool);
+template void Engine<double>::exec_type3(double2 *, double2 *, bool);
 }  // namespace b200

@@ -287,6 +287,18 @@ def test_type3_matches_oracle_and_direct_sum(cuda, oracle, prec, tol, dim):
     hp.setpts(*pts, **dict(zip("stu", frq)))
     hgot = hp.execute(c)
     assert oracle.relerr(hgot.reshape(-1), got.reshape(-1)) <= 1e-5 if prec == "f" else 1e-12
+    # adjoint of type 3 (execute.hpp:515-545): targets -> sources with the conjugate kernel;
+    # checked against the direct sum sum_k F_k exp(-i s_k.x_j) and the identity <F, A c> = <A^H F, c>
+    F_in = _rand_c(rng, (ntr, N), ct)
+    adj = hp.execute_adjoint(F_in)
+    assert adj.shape == (ntr, M)
+    for b in range(ntr):
+        ds = oracle.dirft(3, lf[0], lf[1], lf[2], F_in[b].astype(np.complex128), -1,
+                          s=lp[0], t=lp[1], u=lp[2])
+        assert oracle.relerr(adj[b], ds) <= 10 * tol
+        lhs = np.vdot(F_in[b].astype(np.complex128), hgot[b].astype(np.complex128))
+        rhs = np.vdot(adj[b].astype(np.complex128), c[b].astype(np.complex128))
+        assert abs(lhs - rhs) <= (1e-4 if prec == "f" else 1e-10) * abs(lhs)
     gp.destroy()
     hp.destroy()
 
