@@ -24,6 +24,9 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(src)))
 H = rows[1]; data = rows[2:]
 ia, isamp, isrc = H.index("Instructions Executed"), H.index("# Samples"), H.index("Source")
+for k, r in enumerate(data):  # a report with several launches repeats the table: keep the first
+    if len(r) <= max(ia, isamp, isrc) or not r[ia].strip().isdigit():
+        data = data[:k]; break
 tot = sum(int(r[ia]) for r in data); tots = sum(int(r[isamp]) for r in data)
 print(f"\n# warp-instructions per point = {tot / npts:.2f}; stall samples = {tots}")
 print("# SASS regions (consecutive lines with equal execution count): lines, instr/pt, share of samples, top opcodes")
