@@ -2,7 +2,7 @@
 """bench.py — headline benchmark of the finufft_b200 hot path (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--workload c3_t1|c3_t2|c2_t2|c4_t1] [--M pts] [--dist uniform|cluster]
+                  [--workload c3_t1|c3_t2|c2_t2|c2_t1|c4_t1] [--M pts] [--dist uniform|cluster]
 
 Workload (default c3_t1 = BASELINE.json configs[2], the config the metric is quoted on and
 that fits one GPU): 3D type 1, single precision, 256^3 modes (fine grid 512^3), M = 1e8
@@ -40,6 +40,7 @@ WORKLOADS = {
     "c3_t1": (1, (256, 256, 256), 100_000_000, 1e-6, "complex64", 1),
     "c3_t2": (2, (256, 256, 256), 100_000_000, 1e-6, "complex64", 1),
     "c2_t2": (2, (2048, 2048), 100_000_000, 1e-5, "complex64", 1),
+    "c2_t1": (1, (2048, 2048), 100_000_000, 1e-5, "complex64", 1),
     "c4_t1": (1, (512, 512), 10_000_000, 1e-9, "complex128", 8),
 }
 # type 3 (configs[4]): M sources, N = M targets with frequencies of half-width 107.5 per dim
@@ -371,9 +372,15 @@ def main():
         peak, peak_kind = measured_hbm_peak()
         abytes = algorithmic_bytes(dim, M, nf, rbytes)
         kernel_ms = stage_avg["spreadinterp"] / ntr  # one launch per transform
-        swept = dim == 3 and rbytes == 4 and info["ns"] in (6, 7)
-        kernel_name = (f"k_sweep3<{info['ns']},{'true' if type_ == 1 else 'false'}>" if swept
-                       else ("k_spread" if type_ == 1 else "k_interp"))
+        sweep_on = os.environ.get("B200_NUFFT_SWEEP", "1") != "0"
+        swept = sweep_on and dim == 3 and rbytes == 4 and info["ns"] in (6, 7)
+        tf = "true" if type_ == 1 else "false"
+        if swept:
+            kernel_name = f"k_sweep3<{info['ns']},{tf}>"
+        elif sweep_on and dim == 2:
+            kernel_name = f"k_sweep2<{'float' if rbytes == 4 else 'double'},{info['ns']},{tf}>"
+        else:
+            kernel_name = "k_spread" if type_ == 1 else "k_interp"
         achieved = abytes / (kernel_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": kernel_name,
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

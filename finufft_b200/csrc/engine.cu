@@ -222,6 +222,11 @@ template<class U> struct Scratch {
   Scratch &operator=(const Scratch &) = delete;
 };
 
+static uint32_t sweep2_item_points() {
+  const char *e = getenv("B200_SWEEP2_ITEM");
+  const long v  = e ? atol(e) : 0;
+  return v >= 32 ? (uint32_t)v : kSweep2ItemPoints;
+}
 // refined order inside the bins for the sweep kernels; work units = 512-point chunks of bins
 static void refine_impl(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
                         uint32_t *sidx, const uint32_t *binstart, const GridGeom<float> &g,
@@ -239,6 +244,21 @@ static void refine_impl(int ns, const Packed4<float> *packed, float *xs, float *
 static void refine_impl(int, const Packed4<double> *, double *, double *, double *, uint32_t *,
                         const uint32_t *, const GridGeom<double> &, uint64_t, uint32_t *,
                         cudaStream_t) {}
+// the same for the 2D sweep kernels (any precision)
+template<class T>
+static void refine2_impl(int ns, const Packed4<T> *packed, T *xs, T *ys, uint32_t *sidx,
+                         const uint32_t *binstart, const GridGeom<T> &g, uint64_t M,
+                         uint32_t *scan_tmp, cudaStream_t st) {
+  const uint32_t max_chunks =
+      (uint32_t)(M / kRefineChunk + std::min<uint64_t>(g.nbins, M));
+  Scratch<uint32_t> nch(g.nbins, st), chstart((size_t)g.nbins + 1, st);
+  Scratch<uint32_t> chunk_bin(max_chunks, st), chunk_off(max_chunks, st);
+  launch_sub_count(binstart, g.nbins, kRefineChunk, nch.p, st);
+  exclusive_scan_u32(nch.p, chstart.p, g.nbins, scan_tmp, st);
+  launch_sub_fill(binstart, chstart.p, g.nbins, kRefineChunk, chunk_bin.p, chunk_off.p, st);
+  launch_refine_bins2<T>(ns, packed, xs, ys, sidx, binstart, chunk_bin.p, chunk_off.p,
+                         chstart.p + g.nbins, max_chunks, g, st);
+}
 
 template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z) {
   cudaStream_t st = opts.stream;
@@ -253,6 +273,7 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
   // 3D float with a supported width: the sweep kernels want the order inside the bins refined
   swept_ = std::is_same<T, float>::value && dim == 3 && sweep3_supported(ns) && opts.sweep &&
            nf[0] % 2 == 0 && M > 0;
+  swept2_ = dim == 2 && sweep2_supported<T>(ns) && opts.sweep && M > 0;
   radix_order_ = opts.sort_radix != 0;
 
   if (!radix_order_) {
@@ -266,6 +287,9 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
     if (swept_)
       refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
                   scan_tmp.p, st);
+    else if (swept2_)
+      refine2_impl<T>(ns, packed.p, xs_.p, ys_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
+                      scan_tmp.p, st);
     else
       launch_gather_packed<T>(dim, packed.p, sidx_.p, m, xs_.p, ys_.p, zs_.p, st);
     CU(cudaGetLastError());
@@ -282,19 +306,23 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
     if (which && M)  // result landed in the scratch value buffer
       CU(cudaMemcpyAsync(sidx_.p, vals_b.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToDevice, st));
     launch_bin_bounds(sorted_keys, m, geom.nbins, binstart_.p, st);
-    if (swept_) {
+    if (swept_ || swept2_) {
       Scratch<Packed4<T>> packed(M, st);
       Scratch<uint32_t> keys(M, st), ranks(M, st), cnt(geom.nbins, st);  // packs the coordinates
       CU(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * geom.nbins, st));
       launch_bin_count<T>(dim, x, y, z, m, geom, keys.p, ranks.p, cnt.p, packed.p, st);
-      refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
-                  scan_tmp.p, st);
+      if (swept_)
+        refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
+                    scan_tmp.p, st);
+      else
+        refine2_impl<T>(ns, packed.p, xs_.p, ys_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
+                        scan_tmp.p, st);
     } else
       launch_gather_coords<T>(dim, x, y, z, sidx_.p, m, xs_.p, ys_.p, zs_.p, st);
     CU(cudaGetLastError());
   }
 
-  if (swept_) build_sweep_items(scan_tmp.p);
+  if (swept_ || swept2_) build_sweep_items(scan_tmp.p);
 
   // subproblem list of the generic kernels: every bin in chunks of at most maxsub points
   Scratch<uint32_t> nsubs(geom.nbins, st), substart((size_t)geom.nbins + 1, st);
@@ -318,7 +346,8 @@ template<class T> void Engine<T>::build_sweep_items(uint32_t *scan_tmp) {
   cudaStream_t st = opts.stream;
   const uint32_t nrows = (uint32_t)geom.nb[1] * (uint32_t)geom.nb[2];
   Scratch<uint32_t> nit(nrows, st), itstart((size_t)nrows + 1, st);
-  launch_row_item_count(binstart_.p, nrows, (uint32_t)geom.nb[0], kSweepItemPoints, nit.p, st);
+  const uint32_t maxpts = swept2_ ? sweep2_item_points() : kSweepItemPoints;
+  launch_row_item_count(binstart_.p, nrows, (uint32_t)geom.nb[0], maxpts, nit.p, st);
   exclusive_scan_u32(nit.p, itstart.p, nrows, scan_tmp, st);
   uint32_t total = 0;
   CU(cudaMemcpyAsync(&total, itstart.p + nrows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -326,8 +355,8 @@ template<class T> void Engine<T>::build_sweep_items(uint32_t *scan_tmp) {
   nitems_ = total;
   items_.alloc(std::max<uint32_t>(total, 1));
   if (total)
-    launch_row_item_fill(binstart_.p, itstart.p, nrows, (uint32_t)geom.nb[0], kSweepItemPoints,
-                         items_.p, st);
+    launch_row_item_fill(binstart_.p, itstart.p, nrows, (uint32_t)geom.nb[0], maxpts, items_.p,
+                         st);
 }
 
 template<class T>
@@ -383,6 +412,9 @@ template<class T> void Engine<T>::run_spread(const C *c, C *fw) {
   cudaError_t e;
   if (use_sweep3(fw))
     e = sweep_run(true, const_cast<C *>(c), fw);
+  else if (swept2_)
+    e = launch_spread2_sweep<T>(ns, Sweep2Points<T>{xs_.p, ys_.p, sidx_.p, items_.p, nitems_},
+                                geom, nc, coef.data(), c, fw, opts.stream);
   else if (dim == 1)
     e = launch_spreadinterp<T, 1>(true, ns, pts, geom, nc, coef.data(), c, nullptr, fw, opts.stream);
   else if (dim == 2)
@@ -401,6 +433,9 @@ template<class T> void Engine<T>::run_interp(C *c, const C *fw) {
   C *fwm = const_cast<C *>(fw);
   if (use_sweep3(fw))
     e = sweep_run(false, c, fwm);
+  else if (swept2_)
+    e = launch_interp2_sweep<T>(ns, Sweep2Points<T>{xs_.p, ys_.p, sidx_.p, items_.p, nitems_},
+                                geom, nc, coef.data(), c, fw, opts.stream);
   else if (dim == 1)
     e = launch_spreadinterp<T, 1>(false, ns, pts, geom, nc, coef.data(), nullptr, c, fwm, opts.stream);
   else if (dim == 2)
@@ -494,7 +529,7 @@ template<class T> void Engine<T>::copy_sort_to_host(uint32_t *out) const {
   if (M == 0) return;
   cudaStreamSynchronize(opts.stream);
   cuda_check(cudaMemcpy(out, sidx_.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToHost), "copy sort");
-  if (swept_ || !radix_order_) {
+  if (swept_ || swept2_ || !radix_order_) {
     // The counting sort leaves a bin's points in arrival order and the sweep kernels re-order them; the reference's stable counting sort
     // leaves them in ascending index order (include/finufft/spread.hpp:559-581), which is
     // restored here for inspection.

@@ -21,6 +21,7 @@
 #include "gridops.cuh"
 #include "sort.cuh"
 #include "spreadinterp.cuh"
+#include "sweep2d.cuh"
 
 namespace b200 {
 
@@ -120,6 +121,7 @@ template<class T> class Engine {
   DevBuf<SweepItem> items_;  // 3D float sweep kernels: work items, refined bin order in use
   uint32_t nitems_ = 0;
   bool swept_      = false;
+  bool swept2_     = false;  // 2D sweep kernels (sweep2d.cuh) in use
   bool radix_order_ = false;  // sidx_ is the reference permutation as it stands
   // type 3
   DevBuf<T> xp_[3], sp_[3];

@@ -2,6 +2,7 @@
 // See sort.cuh for the contract and the reference lines the permutation must reproduce.
 #include "devmath.cuh"
 #include "sort.cuh"
+#include "sweep2d.cuh"
 
 namespace b200 {
 
@@ -530,6 +531,128 @@ void launch_refine_bins3(int ns, const Packed4<float> *packed, float *xs, float 
   default: break;
   }
 }
+
+// ---- 2D (sweep2d.cuh): same refinement, any precision and kernel width.  key = gg*5 + jb with
+// gg the x window position relative to the bin's first one (window step S = 1 or 2 cells).
+template<class T> struct Ref2Cfg {
+  static constexpr int WARPS = sizeof(T) == 4 ? 4 : 2;
+  static constexpr int KEYS  = 128;
+};
+
+template<class T, int NS>
+__global__ void __launch_bounds__(Ref2Cfg<T>::WARPS * 32)
+k_refine_bins2(const Packed4<T> *__restrict__ packed, T *__restrict__ xs, T *__restrict__ ys,
+               uint32_t *__restrict__ sidx, const uint32_t *__restrict__ binstart,
+               const uint32_t *__restrict__ chunk_bin, const uint32_t *__restrict__ chunk_off,
+               const uint32_t *__restrict__ nchunks, GridGeom<T> g) {
+  constexpr int WARPS = Ref2Cfg<T>::WARPS, KEYS = Ref2Cfg<T>::KEYS;
+  using WN = Sweep2Win<NS>;
+  constexpr int HL = NS / 2, SH = WN::S - 1, XB = WN::XB, NG = kBinX / WN::S + 2,
+                NJB = kBinY + 1;
+  static_assert(NG * NJB <= KEYS, "key space");
+  __shared__ T sx[WARPS][kRefCap], sy[WARPS][kRefCap];
+  __shared__ uint32_t si[WARPS][kRefCap];
+  __shared__ uint16_t skey[WARPS][kRefCap], sord[WARPS][kRefCap];
+  __shared__ int cnt[WARPS][KEYS + 1], fill[WARPS][KEYS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t nwarps = gridDim.x * WARPS;
+  const uint32_t total  = *nchunks;
+  for (uint32_t ch = blockIdx.x * WARPS + warp; ch < total; ch += nwarps) {
+    const uint32_t bin = chunk_bin[ch], q0 = chunk_off[ch];
+    const int i1 = bin % g.nb[0], i2 = bin / g.nb[0];
+    const int n  = (int)min((uint32_t)kRefCap, binstart[bin + 1] - q0);
+    const int gbase = (kBinX * i1 - HL + XB) >> SH;
+#pragma unroll
+    for (int k = 0; k < KEYS / 32; ++k) cnt[warp][lane + 32 * k] = 0, fill[warp][lane + 32 * k] = 0;
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) {
+      const uint32_t j    = sidx[q0 + k];
+      const Packed4<T> pt = packed[j];
+      sx[warp][k] = pt.x, sy[warp][k] = pt.y, si[warp][k] = j;
+      int i0, j0;
+      T t;
+      stencil_start<T, NS>(fold_rescale<T>(pt.x, g.nf_t[0]), i0, t);
+      stencil_start<T, NS>(fold_rescale<T>(pt.y, g.nf_t[1]), j0, t);
+      const int gg  = min(max(((i0 + XB) >> SH) - gbase, 0), NG - 1);
+      const int jb  = min(max(j0 - (kBinY * i2 - HL), 0), kBinY);
+      const int key = gg * NJB + jb;
+      skey[warp][k] = (uint16_t)key;
+      atomicAdd(&cnt[warp][key], 1);
+    }
+    __syncwarp();
+    {  // exclusive scan of the KEYS counters, KEYS/32 per lane; cnt[KEYS] = n
+      constexpr int PL = KEYS / 32;
+      int v[PL], sum = 0;
+#pragma unroll
+      for (int k = 0; k < PL; ++k) v[k] = cnt[warp][PL * lane + k], sum += v[k];
+      int incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+      }
+      __syncwarp();
+      int run = incl - sum;
+#pragma unroll
+      for (int k = 0; k < PL; ++k) cnt[warp][PL * lane + k] = run, run += v[k];
+      if (lane == 31) cnt[warp][KEYS] = incl;
+    }
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) {
+      const int key = skey[warp][k];
+      sord[warp][cnt[warp][key] + atomicAdd(&fill[warp][key], 1)] = (uint16_t)k;
+    }
+    __syncwarp();
+    for (int p = lane; p < n; p += 32) {
+      const int k = sord[warp][p], key = skey[warp][k];
+      const uint32_t mine = si[warp][k];
+      const int b0 = cnt[warp][key], b1 = cnt[warp][key + 1];
+      int r = 0;
+      for (int q = b0; q < b1; ++q) r += si[warp][sord[warp][q]] < mine ? 1 : 0;
+      const uint32_t dst = q0 + b0 + r;
+      xs[dst] = sx[warp][k], ys[dst] = sy[warp][k], sidx[dst] = mine;
+    }
+    __syncwarp();
+  }
+}
+
+template<class T, int NS>
+static void refine2_ns(const Packed4<T> *packed, T *xs, T *ys, uint32_t *sidx,
+                       const uint32_t *binstart, const uint32_t *chunk_bin,
+                       const uint32_t *chunk_off, const uint32_t *nchunks, uint32_t max_chunks,
+                       const GridGeom<T> &g, cudaStream_t st) {
+  constexpr int WARPS = Ref2Cfg<T>::WARPS;
+  const int nb = grid_for((max_chunks + WARPS - 1) / WARPS * 32 * WARPS, WARPS * 32, 16);
+  k_refine_bins2<T, NS><<<nb, WARPS * 32, 0, st>>>(packed, xs, ys, sidx, binstart, chunk_bin,
+                                                   chunk_off, nchunks, g);
+}
+template<class T>
+void launch_refine_bins2(int ns, const Packed4<T> *packed, T *xs, T *ys, uint32_t *sidx,
+                         const uint32_t *binstart, const uint32_t *chunk_bin,
+                         const uint32_t *chunk_off, const uint32_t *nchunks, uint32_t max_chunks,
+                         const GridGeom<T> &g, cudaStream_t st) {
+  if (max_chunks == 0) return;
+  switch (ns) {
+#define B200_REF2(NSV)                                                                         \
+  case NSV:                                                                                    \
+    refine2_ns<T, NSV>(packed, xs, ys, sidx, binstart, chunk_bin, chunk_off, nchunks,          \
+                       max_chunks, g, st);                                                     \
+    break;
+    B200_REF2(2) B200_REF2(3) B200_REF2(4) B200_REF2(5) B200_REF2(6) B200_REF2(7) B200_REF2(8)
+    B200_REF2(9) B200_REF2(10) B200_REF2(11) B200_REF2(12) B200_REF2(13) B200_REF2(14)
+    B200_REF2(15) B200_REF2(16)
+#undef B200_REF2
+  default: break;
+  }
+}
+template void launch_refine_bins2<float>(int, const Packed4<float> *, float *, float *, uint32_t *,
+                                         const uint32_t *, const uint32_t *, const uint32_t *,
+                                         const uint32_t *, uint32_t, const GridGeom<float> &,
+                                         cudaStream_t);
+template void launch_refine_bins2<double>(int, const Packed4<double> *, double *, double *,
+                                          uint32_t *, const uint32_t *, const uint32_t *,
+                                          const uint32_t *, const uint32_t *, uint32_t,
+                                          const GridGeom<double> &, cudaStream_t);
 
 __global__ void k_row_item_count(const uint32_t *__restrict__ binstart, uint32_t nrows,
                                  uint32_t nb1, uint32_t maxpts, uint32_t *__restrict__ nitems) {

@@ -8,6 +8,7 @@ the full BASELINE sizes, size-independent properties (stable-sortedness of the p
 type-1/type-2 adjointness, linearity, spread mass conservation).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -207,6 +208,91 @@ def test_spreadinterp_only(cuda, oracle):
             ci = ip.execute(cuda.from_numpy(g).cuda()).cpu().numpy()
             wanti = oracle.interp(list(grid[::-1]), lp[0], lp[1], lp[2], g.reshape(-1), perm, coef)
             assert oracle.relerr(ci, wanti) < (2e-6 if prec == "f" else 1e-14)
+
+
+def _ns_of(oracle, tol, sigma, rt):
+    return oracle.kernel_setup(tol, 2, 1, sigma, rt, True)[1]
+
+
+# (precision, tol, sigma): together they hit every kernel width the 2D sweep kernels are built
+# for (float 2..12, double 2..16), both window layouts (8 / 16 lanes) and both window steps
+SWEEP2_WIDTHS = [("f", t, 2.0) for t in (3e-1, 3e-3, 1e-3, 3e-4, 3e-5, 3e-6, 2e-7)] + \
+                [("f", t, 1.25) for t in (1e-3, 1e-4, 1e-5)] + \
+                [("d", t, 2.0) for t in (1e-1, 3e-3, 1e-3, 3e-4, 1e-5, 3e-6, 1e-7, 1e-8, 1e-9,
+                                         1e-10, 1e-11, 1e-12, 1e-13, 1e-14, 1e-15)] + \
+                [("d", t, 1.25) for t in (1e-6, 1e-7, 1e-8, 1e-9)]
+
+
+@pytest.mark.parametrize("kind", ["uniform", "cluster", "edges"])
+def test_sweep2d_stage_parity_all_widths(cuda, oracle, kind):
+    """2D row-sweep kernels (sweep2d.cuh), spread-only and interp-only, against the oracle's
+    spread / interp on the same points, for every kernel width; plus the generic kernels
+    (B200_NUFFT_SWEEP=0) as a second opinion."""
+    import finufft_b200 as F
+    rng = np.random.default_rng(55)
+    grid, M = (96, 72), 30_000
+    seen = set()
+    for prec, tol, sigma in SWEEP2_WIDTHS:
+        rt, ct = _dt(prec)
+        err, ns, beta, tolu = oracle.kernel_setup(tol, 2, 1, sigma, rt, True)
+        assert err == 0
+        seen.add((prec, ns))
+        coef, _ = oracle.horner(ns, beta, tolu, rt)
+        pts = make_points(rng, 2, M, rt, kind, nf=grid)[:2]
+        lp = pts[::-1] + [None]
+        perm, _ = oracle.bin_sort(lp[0], lp[1], lp[2], list(grid[::-1]))
+        c = _rand_c(rng, (M,), ct)
+        g = _rand_c(rng, grid, ct)
+        want_s = oracle.spread(list(grid[::-1]), lp[0], lp[1], lp[2], c, perm, coef)
+        want_i = oracle.interp(list(grid[::-1]), lp[0], lp[1], lp[2], g.reshape(-1), perm, coef)
+        bar = (3e-6 if kind == "uniform" else 3e-5) if prec == "f" else 1e-13
+        dpts = [cuda.from_numpy(p).cuda() for p in pts]
+        for sweep in ("1", "0"):
+            os.environ["B200_NUFFT_SWEEP"] = sweep
+            try:
+                sp = F.Plan(1, grid, 1, tol, 1, ct, upsampfac=sigma, gpu_spreadinterponly=1)
+                sp.setpts(*dpts)
+                assert sp.info()["ns"] == ns
+                fw = sp.execute(cuda.from_numpy(c).cuda()).cpu().numpy()
+                ip = F.Plan(2, grid, 1, tol, 1, ct, upsampfac=sigma, gpu_spreadinterponly=1)
+                ip.setpts(*dpts)
+                ci = ip.execute(cuda.from_numpy(g).cuda()).cpu().numpy()
+            finally:
+                os.environ.pop("B200_NUFFT_SWEEP", None)
+            assert oracle.relerr(fw, want_s) < bar, (prec, ns, sigma, sweep, "spread")
+            assert oracle.relerr(ci, want_i) < bar, (prec, ns, sigma, sweep, "interp")
+            sp.destroy()
+            ip.destroy()
+    assert {n for p_, n in seen if p_ == "f"} >= set(range(2, 9))
+    assert {n for p_, n in seen if p_ == "d"} >= set(range(3, 16))
+
+
+def test_sweep2d_ragged_and_batched(cuda, oracle):
+    """Few points (fewer than a chunk, one point, none), many vectors, odd grid sizes."""
+    import finufft_b200 as F
+    rng = np.random.default_rng(56)
+    for prec, tol in (("f", 1e-5), ("d", 1e-10)):
+        rt, ct = _dt(prec)
+        for modes, M, ntr in (((37, 21), 1, 1), ((37, 21), 31, 3), ((16, 90), 33, 2),
+                              ((50, 64), 7000, 4)):
+            for type_ in (1, 2):
+                gp, op = _plans(F, oracle, type_, modes, ntr, tol, prec)
+                pts = make_points(rng, 2, M, rt, "wide")[:2]
+                gp.setpts(*[cuda.from_numpy(p).cuda() for p in pts])
+                op.setpts(pts[1], pts[0], None)
+                shape = (M,) if type_ == 1 else modes
+                data = _rand_c(rng, ((ntr,) if ntr > 1 else ()) + shape, ct)
+                got = gp.execute(cuda.from_numpy(data).cuda()).cpu().numpy()
+                want = op.execute(data)
+                assert oracle.relerr(got, want) <= 2 * tol, (prec, modes, M, ntr, type_)
+                gp.destroy()
+        gp = F.Plan(1, (20, 20), 1, tol, 1, ct, upsampfac=2.0)
+        gp.setpts(cuda.zeros(0, dtype=cuda.float32 if prec == "f" else cuda.float64, device="cuda"),
+                  cuda.zeros(0, dtype=cuda.float32 if prec == "f" else cuda.float64, device="cuda"))
+        out = gp.execute(cuda.zeros(0, dtype=cuda.complex64 if prec == "f" else cuda.complex128,
+                                    device="cuda"))
+        assert float(out.abs().max()) == 0.0
+        gp.destroy()
 
 
 def test_many_points_in_one_bin(cuda, oracle):
