@@ -21,14 +21,17 @@ template<class T, int NS, bool SPREAD> struct Sweep2Cfg {
   static constexpr int CH  = 32;                  // points per chunk: one per lane
   static constexpr int WPB = 4;                   // warps (= work items) per block
   static constexpr int KV  = 16 / (int)sizeof(T);  // values per 16-byte shared-memory access
-  static constexpr int KP  = (NS + KV - 1) / KV * KV;  // y-window record pitch
+  // y-window record of a point: its NS values placed at the rows of the register window they
+  // multiply (offset jb = stencil start inside the bin row), zeros elsewhere
+  static constexpr int KP  = (YR + KV - 1) / KV * KV;
   // x-window record [slot][point]: pitch chosen so that the lanes of one shared-memory phase
   // (128 bytes) read distinct banks: lane (g, a) reads slot a of point q+g
   static constexpr int LPP = 128 / (int)sizeof(XE);
   static constexpr int XP  = CH + (LPP / W > 1 ? LPP / W : 1);
   static constexpr size_t KY_BYTES  = (size_t)CH * KP * sizeof(T);
   static constexpr size_t XW_BYTES  = ((size_t)W * XP * sizeof(XE) + 15) / 16 * 16;
-  static constexpr size_t OUT_BYTES = SPREAD ? 0 : (size_t)CH * sizeof(C);
+  // interp: the W per-column shares of every point, summed thread-per-point after the chunk
+  static constexpr size_t OUT_BYTES = SPREAD ? 0 : (size_t)CH * W * sizeof(C);
   static constexpr size_t WARP_BYTES = KY_BYTES + XW_BYTES + OUT_BYTES;
 };
 
@@ -46,9 +49,8 @@ template<class T> __device__ __forceinline__ T shfl_xor_t(T v, int d) {
   return __shfl_xor_sync(0xffffffffu, v, d);
 }
 
-// NS window values of one point from its 16-byte aligned record
-template<class T, int NS, int KP>
-__device__ __forceinline__ void load_ky(const T *rec, T (&ky)[KP]) {
+// the padded y record of one point (16-byte aligned)
+template<class T, int KP> __device__ __forceinline__ void load_ky(const T *rec, T (&ky)[KP]) {
   constexpr int KV = 16 / (int)sizeof(T);
 #pragma unroll
   for (int v = 0; v < KP / KV; ++v) {
@@ -62,44 +64,65 @@ __device__ __forceinline__ void load_ky(const T *rec, T (&ky)[KP]) {
   }
 }
 
-// points [p, e) of the current chunk, all with y stencil start J: every lane group takes one
-template<class T, int NS, int J, class CF>
-__device__ __forceinline__ void spread_run2(typename CF::C (&acc)[CF::YR], const T *sky,
-                                            const typename CF::C *sxw, int p, int e, int g,
-                                            int la) {
-  for (int q = p; q < e; q += CF::G) {
-    const int idx = q + g;
-    if (idx < e) {
-      T ky[CF::KP];
-      load_ky<T, NS, CF::KP>(sky + idx * CF::KP, ky);
-      const typename CF::C cw = sxw[la * CF::XP + idx];
+// One step: lane group g handles point idx of the chunk.  The two-point forms issue the
+// shared-memory loads of both points before any arithmetic.
+template<class T, class CF>
+__device__ __forceinline__ void spread_math2(typename CF::C (&acc)[CF::YR], const T (&ky)[CF::KP],
+                                             typename CF::C cw) {
 #pragma unroll
-      for (int t = 0; t < NS; ++t) acc[J + t] = cx_fma(ky[t], cw, acc[J + t]);
-    }
-  }
+  for (int r = 0; r < CF::YR; ++r) acc[r] = cx_fma(ky[r], cw, acc[r]);
 }
-template<class T, int NS, int J, class CF>
-__device__ __forceinline__ void interp_run2(const typename CF::C (&acc)[CF::YR], const T *sky,
-                                            const T *sxw, typename CF::C *sout, int p, int e,
-                                            int g, int la) {
-  for (int q = p; q < e; q += CF::G) {
-    const int idx    = q + g;
-    const bool valid = idx < e;
-    const int idc    = valid ? idx : p;
-    T ky[CF::KP];
-    load_ky<T, NS, CF::KP>(sky + idc * CF::KP, ky);
-    const T wx          = sxw[la * CF::XP + idc];
-    typename CF::C v = cx_mul(ky[0], acc[J]);
+template<class T, class CF>
+__device__ __forceinline__ void spread_step2(typename CF::C (&acc)[CF::YR], const T *sky,
+                                             const typename CF::C *sxw, int idx, int la) {
+  T ky[CF::KP];
+  load_ky<T, CF::KP>(sky + idx * CF::KP, ky);
+  spread_math2<T, CF>(acc, ky, sxw[la * CF::XP + idx]);
+}
+template<class T, class CF>
+__device__ __forceinline__ void spread_step2x2(typename CF::C (&acc)[CF::YR], const T *sky,
+                                               const typename CF::C *sxw, int idx, int la) {
+  T ka[CF::KP], kb[CF::KP];
+  load_ky<T, CF::KP>(sky + idx * CF::KP, ka);
+  load_ky<T, CF::KP>(sky + (idx + CF::G) * CF::KP, kb);
+  const typename CF::C ca = sxw[la * CF::XP + idx], cb = sxw[la * CF::XP + idx + CF::G];
+  spread_math2<T, CF>(acc, ka, ca);
+  spread_math2<T, CF>(acc, kb, cb);
+}
+template<class T, class CF>
+__device__ __forceinline__ typename CF::C interp_math2(const typename CF::C (&acc)[CF::YR],
+                                                       const T (&ky)[CF::KP], T wx) {
+  // two independent chains halve the dependent-FMA latency
+  typename CF::C v0 = cx_mul(ky[0], acc[0]), v1 = cx_mul(ky[1], acc[1]);
 #pragma unroll
-    for (int t = 1; t < NS; ++t) v = cx_fma(ky[t], acc[J + t], v);
-    v = cx_mul(wx, v);
-#pragma unroll
-    for (int d = 1; d < CF::W; d <<= 1) {
-      v.x += shfl_xor_t(v.x, d);
-      v.y += shfl_xor_t(v.y, d);
-    }
-    if (valid && la == 0) sout[idx] = v;
+  for (int r = 2; r + 1 < CF::YR; r += 2) {
+    v0 = cx_fma(ky[r], acc[r], v0);
+    v1 = cx_fma(ky[r + 1], acc[r + 1], v1);
   }
+  if constexpr (CF::YR % 2 == 1) v0 = cx_fma(ky[CF::YR - 1], acc[CF::YR - 1], v0);
+  v0.x += v1.x, v0.y += v1.y;
+  return cx_mul(wx, v0);
+}
+template<class T, class CF>
+__device__ __forceinline__ void interp_step2(const typename CF::C (&acc)[CF::YR], const T *sky,
+                                             const T *sxw, typename CF::C *spart, int idx,
+                                             int la) {
+  T ky[CF::KP];
+  load_ky<T, CF::KP>(sky + idx * CF::KP, ky);
+  spart[idx * CF::W + la] = interp_math2<T, CF>(acc, ky, sxw[la * CF::XP + idx]);
+}
+template<class T, class CF>
+__device__ __forceinline__ void interp_step2x2(const typename CF::C (&acc)[CF::YR], const T *sky,
+                                               const T *sxw, typename CF::C *spart, int idx,
+                                               int la) {
+  T ka[CF::KP], kb[CF::KP];
+  load_ky<T, CF::KP>(sky + idx * CF::KP, ka);
+  load_ky<T, CF::KP>(sky + (idx + CF::G) * CF::KP, kb);
+  const T wa = sxw[la * CF::XP + idx], wb = sxw[la * CF::XP + idx + CF::G];
+  const typename CF::C va = interp_math2<T, CF>(acc, ka, wa);
+  const typename CF::C vb = interp_math2<T, CF>(acc, kb, wb);
+  spart[idx * CF::W + la]           = va;
+  spart[(idx + CF::G) * CF::W + la] = vb;
 }
 
 // One warp per work item: a run of consecutive points of one row of bins (i2), which the
@@ -117,7 +140,7 @@ k_sweep2(const Sweep2Args<T, NS> a) {
   unsigned char *base = smem + (size_t)warp * CF::WARP_BYTES;
   T *sky   = reinterpret_cast<T *>(base);
   XE *sxw  = reinterpret_cast<XE *>(base + CF::KY_BYTES);
-  C *sout  = reinterpret_cast<C *>(base + CF::KY_BYTES + CF::XW_BYTES);
+  C *spart = reinterpret_cast<C *>(base + CF::KY_BYTES + CF::XW_BYTES);
 
   const int g = lane / CF::W, la = lane % CF::W;
   const SweepItem item = a.pts.items[it];
@@ -208,7 +231,7 @@ k_sweep2(const Sweep2Args<T, NS> a) {
     if (lane < nc) {
       int i0;
       T x1;
-      T kv[CF::KP + 2];
+      T kv[NS + 2];
       stencil_start<T, NS>(fold_rescale<T>(cur.x, a.g.nf_t[0]), i0, x1);
       eval_window_t(a.tab, x1, kv);
       const int gpos = (i0 + CF::XB) >> (CF::S - 1);
@@ -223,21 +246,20 @@ k_sweep2(const Sweep2Args<T, NS> a) {
       int j0;
       stencil_start<T, NS>(fold_rescale<T>(cur.y, a.g.nf_t[1]), j0, x1);
       eval_window_t(a.tab, x1, kv);
-#pragma unroll
-      for (int t = NS; t < CF::KP; ++t) kv[t] = (T)0;
-      T *rk = sky + lane * CF::KP;
+      const int jb = min(max(j0 - (kBinY * i2 - CF::HL), 0), kBinY);
+      T *rk        = sky + lane * CF::KP;
 #pragma unroll
       for (int v = 0; v < CF::KP / CF::KV; ++v) {
         if constexpr (sizeof(T) == 4)
-          *reinterpret_cast<float4 *>(rk + 4 * v) =
-              make_float4(kv[4 * v], kv[4 * v + 1], kv[4 * v + 2], kv[4 * v + 3]);
+          *reinterpret_cast<float4 *>(rk + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
         else
-          *reinterpret_cast<double2 *>(rk + 2 * v) = make_double2(kv[2 * v], kv[2 * v + 1]);
+          *reinterpret_cast<double2 *>(rk + 2 * v) = make_double2(0.0, 0.0);
       }
-      const int jb = min(max(j0 - (kBinY * i2 - CF::HL), 0), kBinY);
-      key          = gpos * 8 + jb;
+#pragma unroll
+      for (int t = 0; t < NS; ++t) rk[jb + t] = kv[t];
+      key = gpos;
     }
-    // runs of equal key: bit l of heads = point l starts a run
+    // runs of equal window position: bit l of heads = point l starts a run
     const int prev       = __shfl_up_sync(0xffffffffu, key, 1);
     const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
     __syncwarp();
@@ -248,21 +270,28 @@ k_sweep2(const Sweep2Args<T, NS> a) {
       const uint32_t rest = p < 31 ? heads >> (p + 1) : 0u;
       int e               = rest ? p + __ffs(rest) : 32;
       e                   = min(e, nc);
-      advance_to(CF::S * (kp >> 3) - CF::XB);
-#define B200_RUN2(J)                                                              \
-  case J:                                                                         \
-    if constexpr (SPREAD) spread_run2<T, NS, J, CF>(acc, sky, sxw, p, e, g, la);  \
-    else interp_run2<T, NS, J, CF>(acc, sky, sxw, sout, p, e, g, la);             \
-    break;
-      switch (kp & 7) {
-        B200_RUN2(0) B200_RUN2(1) B200_RUN2(2) B200_RUN2(3) B200_RUN2(4)
-      default: break;
+      advance_to(CF::S * kp - CF::XB);
+      int q = p;
+      for (; q + 2 * CF::G <= e; q += 2 * CF::G) {  // two full steps: loads of both overlap
+        if constexpr (SPREAD) spread_step2x2<T, CF>(acc, sky, sxw, q + g, la);
+        else interp_step2x2<T, CF>(acc, sky, sxw, spart, q + g, la);
       }
-#undef B200_RUN2
+      for (; q < e; q += CF::G) {
+        if (q + g < e) {
+          if constexpr (SPREAD) spread_step2<T, CF>(acc, sky, sxw, q + g, la);
+          else interp_step2<T, CF>(acc, sky, sxw, spart, q + g, la);
+        }
+      }
       p = e;
     }
     __syncwarp();
-    if (!SPREAD && lane < nc) a.c_out[cur.j] = sout[lane];
+    if (!SPREAD && lane < nc) {  // lane = point: add the W column shares, scatter
+      const C *pp = spart + lane * CF::W;
+      C s0 = pp[0];
+#pragma unroll
+      for (int k = 1; k < CF::W; ++k) s0.x += pp[k].x, s0.y += pp[k].y;
+      a.c_out[cur.j] = s0;
+    }
     __syncwarp();
   }
   empty_window();

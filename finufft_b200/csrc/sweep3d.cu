@@ -1,6 +1,8 @@
 // Row-sweep spread / interp kernels for 3D float (see sweep3d.cuh for the design).
 #include "sweep3d.cuh"
 
+#include "sweepmath.cuh"
+
 #include <limits.h>
 #include <stdlib.h>
 
@@ -8,25 +10,6 @@
 
 namespace b200 {
 
-// (re,im) = s * (wr,wi) + (ar,ai): one packed FFMA2 (the scalar operand is broadcast in hardware)
-__device__ __forceinline__ float2 ffma2_s(float s, float2 w, float2 acc) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rc, rd;\n"
-      " mov.b64 ra, {%2,%2};\n mov.b64 rb, {%3,%4};\n mov.b64 rc, {%5,%6};\n"
-      " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0,%1}, rd;}\n"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(s), "f"(w.x), "f"(w.y), "f"(acc.x), "f"(acc.y));
-  return d;
-}
-__device__ __forceinline__ float2 fmul2_s(float s, float2 w) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rd;\n"
-      " mov.b64 ra, {%2,%2};\n mov.b64 rb, {%3,%4};\n"
-      " mul.rn.f32x2 rd, ra, rb;\n mov.b64 {%0,%1}, rd;}\n"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(s), "f"(w.x), "f"(w.y));
-  return d;
-}
 template<int OFF> __device__ __forceinline__ void sts64(uint32_t addr, float2 v) {
   asm volatile("st.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(addr), "n"(OFF), "f"(v.x), "f"(v.y)
                : "memory");
@@ -36,14 +19,6 @@ template<int OFF> __device__ __forceinline__ float2 lds64(uint32_t addr) {
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "n"(OFF));
   return v;
 }
-// statically unrolled loop with the index available as a compile-time constant
-template<int I, int N, class F> __device__ __forceinline__ void static_for(F &&f) {
-  if constexpr (I < N) {
-    f(std::integral_constant<int, I>{});
-    static_for<I + 1, N>(f);
-  }
-}
-
 template<int NS> struct SweepCfg {
   static constexpr int HL   = NS / 2;               // cells left of a bin a stencil can reach
   static constexpr int W    = 8;                    // x rows of the register window
@@ -256,20 +231,26 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
   // interp: two new x rows enter at the far end, their owners pick them up from staging.
   auto slide = [&]() {
     if (SPREAD) {
-      const int r0 = jw & 7, r1 = (jw + 1) & 7;
-      if (la == r0 || la == r1) {
-        const uint32_t dst =
-            my_stage + (uint32_t)((jw - sbase + (la == r1 ? 1 : 0)) * sizeof(float2));
+      const int rel   = (la - jw) & 7;  // this lane's row is jw + rel
+      const int leave = rel < 2;
+      if (leave) {
+        const uint32_t dst = my_stage + (uint32_t)((jw - sbase + rel) * sizeof(float2));
         static_for<0, CF::RZ>([&](auto mc) {
           constexpr int m = decltype(mc)::value;
           static_for<0, CF::YR>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             if ((m + 1) * CF::BQ <= CF::ZT || bq + m * CF::BQ < CF::ZT)
               sts64<(m * CF::BQ * CF::YR + c) * CF::SX * (int)sizeof(float2)>(dst, acc[m][c]);
-            acc[m][c] = float2{0.f, 0.f};
           });
         });
       }
+      // clear the rows that left: one packed multiply per accumulator, no branch, so the
+      // accumulators stay in place (a select costs two instructions per accumulator)
+      const float keep = leave ? 0.f : 1.f;
+#pragma unroll
+      for (int m = 0; m < CF::RZ; ++m)
+#pragma unroll
+        for (int c = 0; c < CF::YR; ++c) acc[m][c] = fmul2_s(keep, acc[m][c]);
       jw += 2;
       if (jw - sbase == CF::SX) {
         flush_stage(CF::SX);

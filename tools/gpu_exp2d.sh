@@ -1,31 +1,26 @@
 #!/bin/bash
 # 2D sweep kernels: parity tests, then A/B timing against the generic kernels.
 out=gpurun_out; mkdir -p $out
-timeout 900 python -m pytest tests -m gpu -x -q > $out/x2d_pytest.log 2>&1; echo "pytest exit $?" >> $out/x2d_pytest.log
-tail -5 $out/x2d_pytest.log
-for w in c2_t2 c2_t1 c4_t1; do
-  for sw in 1 0; do
-    B200_NUFFT_SWEEP=$sw timeout 300 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > $out/x2d_${w}_sw$sw.json 2> $out/x2d_${w}_sw$sw.err
-    python - <<PY
+tag=${1:-x2d}
+timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log
+tail -5 $out/${tag}_pytest.log
+show() {
+python - <<PY
 import json
 try:
-    d=json.loads(open("$out/x2d_${w}_sw$sw.json").read().strip().splitlines()[-1])
-    print("$w sweep=$sw", "ms/step %.3f"%d["ms_per_step"], d["stages_ms"], "setpts %.2f"%d["setpts_ms"], "frac %.3f"%d["roofline"]["frac"], "e2e %.3g"%d["e2e"]["value"])
+    d=json.loads(open("$1").read().strip().splitlines()[-1])
+    print("$2", "ms/step %.3f"%d["ms_per_step"], {k: round(v,3) for k,v in d["stages_ms"].items()}, "setpts %.2f"%d["setpts_ms"], "frac %.3f"%d["roofline"]["frac"], "e2e %.3g"%d["e2e"]["value"])
 except Exception as e:
-    print("$w sweep=$sw FAILED", e); print(open("$out/x2d_${w}_sw$sw.err").read()[-1500:])
+    print("$2 FAILED", e)
 PY
-  done
+}
+for w in c2_t2 c2_t1 c4_t1 c3_t1 c3_t2; do
+  timeout 300 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > $out/${tag}_${w}.json 2> $out/${tag}_${w}.err
+  show $out/${tag}_${w}.json "$w"
 done
-for it in 1024 2048 8192 16384; do
+for it in 1024 2048; do
   for w in c2_t2 c2_t1; do
-    B200_SWEEP2_ITEM=$it timeout 300 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > $out/x2d_${w}_it$it.json 2>/dev/null
-    python - <<PY
-import json
-try:
-    d=json.loads(open("$out/x2d_${w}_it$it.json").read().strip().splitlines()[-1])
-    print("$w item=$it", "ms/step %.3f"%d["ms_per_step"], d["stages_ms"], "setpts %.2f"%d["setpts_ms"])
-except Exception as e:
-    print("$w item=$it FAILED", e)
-PY
+    B200_SWEEP2_ITEM=$it timeout 300 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > $out/${tag}_${w}_it$it.json 2>/dev/null
+    show $out/${tag}_${w}_it$it.json "$w item=$it"
   done
 done
