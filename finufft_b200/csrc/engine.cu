@@ -88,6 +88,7 @@ Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr
   if (opts.maxsub < 32) opts.maxsub = 32;
   if (const char *env = getenv("B200_NUFFT_SWEEP")) opts.sweep = atoi(env);  // debugging aids
   if (const char *env = getenv("B200_NUFFT_SORT")) opts.sort_radix = atoi(env) == 2;
+  if (const char *env = getenv("B200_NUFFT_STAGE")) opts.stage = atoi(env);
   plan_kernel();
   if (type != 3) {
     for (int d = 0; d < dim; ++d) ms[d] = nmodes[d];
@@ -323,6 +324,7 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
   }
 
   if (swept_ || swept2_) build_sweep_items(scan_tmp.p);
+  build_staging();
 
   // subproblem list of the generic kernels: every bin in chunks of at most maxsub points
   Scratch<uint32_t> nsubs(geom.nbins, st), substart((size_t)geom.nbins + 1, st);
@@ -340,6 +342,30 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
                     sub_off_.p, st);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(st));
+}
+
+// Two-level permutation (stage.cuh): worth it once the strength vector is far larger than the
+// L2, where every random 8/16-byte access costs a 128-byte line of HBM traffic.
+template<class T> void Engine<T>::build_staging() {
+  cudaStream_t st = opts.stream;
+  const uint64_t bytes = (uint64_t)M * sizeof(C);
+  staged_ = opts.stage > 0 || (opts.stage < 0 && bytes > (96ull << 20));
+  if (M == 0) staged_ = false;
+  if (!staged_) return;
+  int shift = stage_shift((uint64_t)M, (int)sizeof(C));
+  if (const char *env = getenv("B200_NUFFT_STAGE_SHIFT")) {  // tests: many windows at small M
+    shift = std::max(1, atoi(env));
+    while ((((uint64_t)M + (1ull << shift) - 1) >> shift) > (uint64_t)kStageMaxWindows) ++shift;
+  }
+  const uint32_t nunits = ((uint32_t)M + kStageUnit - 1) / kStageUnit;
+  const size_t ncnt     = (size_t)kStageMaxWindows * nunits;
+  Scratch<uint32_t> counts(ncnt, st), offsets(ncnt + 1, st), tmp(ncnt / 4096 + 8, st);
+  perm1_.alloc(M);
+  perm2_.alloc(M);
+  mid_.alloc(M);
+  build_stage_perms(sidx_.p, (uint32_t)M, shift, counts.p, offsets.p, tmp.p, perm1_.p, perm2_.p,
+                    st);
+  CU(cudaGetLastError());
 }
 
 template<class T> void Engine<T>::build_sweep_items(uint32_t *scan_tmp) {
@@ -400,9 +426,10 @@ static cudaError_t sweep_impl(bool, int, const SweepPoints &, const GridGeom<dou
                               const double *, double2 *, double2 *, cudaStream_t) {
   return cudaErrorInvalidValue;
 }
-template<class T> cudaError_t Engine<T>::sweep_run(bool spread, C *c, C *fw) {
+template<class T>
+cudaError_t Engine<T>::sweep_run(bool spread, C *c, C *fw, const uint32_t *ix) {
   SweepPoints sp{reinterpret_cast<const float *>(xs_.p), reinterpret_cast<const float *>(ys_.p),
-                 reinterpret_cast<const float *>(zs_.p), sidx_.p, items_.p, nitems_};
+                 reinterpret_cast<const float *>(zs_.p), ix, items_.p, nitems_};
   return sweep_impl(spread, ns, sp, geom, nc, coef.data(), c, fw, opts.stream);
 }
 template<class T> void Engine<T>::run_spread(const C *c, C *fw) {
@@ -410,11 +437,19 @@ template<class T> void Engine<T>::run_spread(const C *c, C *fw) {
   PointSet<T> pts{xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, sub_bin_.p, sub_off_.p, nsub,
                   (uint32_t)opts.maxsub};
   cudaError_t e;
+  const uint32_t *ix = sidx_.p;
+  if (staged_) {  // strengths grouped by window of the user index; kernels then index mid
+    launch_stage_in<C>(c, perm2_.p, mid_.p, (uint32_t)M, opts.stream);
+    ++launches;
+    c  = mid_.p;
+    ix = perm1_.p;
+    pts.sidx = ix;
+  }
   if (use_sweep3(fw))
-    e = sweep_run(true, const_cast<C *>(c), fw);
+    e = sweep_run(true, const_cast<C *>(c), fw, ix);
   else if (swept2_)
-    e = launch_spread2_sweep<T>(ns, Sweep2Points<T>{xs_.p, ys_.p, sidx_.p, items_.p, nitems_},
-                                geom, nc, coef.data(), c, fw, opts.stream);
+    e = launch_spread2_sweep<T>(ns, Sweep2Points<T>{xs_.p, ys_.p, ix, items_.p, nitems_}, geom,
+                                nc, coef.data(), c, fw, opts.stream);
   else if (dim == 1)
     e = launch_spreadinterp<T, 1>(true, ns, pts, geom, nc, coef.data(), c, nullptr, fw, opts.stream);
   else if (dim == 2)
@@ -431,11 +466,18 @@ template<class T> void Engine<T>::run_interp(C *c, const C *fw) {
                   (uint32_t)opts.maxsub};
   cudaError_t e;
   C *fwm = const_cast<C *>(fw);
+  C *cuser = c;
+  const uint32_t *ix = sidx_.p;
+  if (staged_) {  // kernels write mid in window order; stage_out scatters inside the windows
+    c  = mid_.p;
+    ix = perm1_.p;
+    pts.sidx = ix;
+  }
   if (use_sweep3(fw))
-    e = sweep_run(false, c, fwm);
+    e = sweep_run(false, c, fwm, ix);
   else if (swept2_)
-    e = launch_interp2_sweep<T>(ns, Sweep2Points<T>{xs_.p, ys_.p, sidx_.p, items_.p, nitems_},
-                                geom, nc, coef.data(), c, fw, opts.stream);
+    e = launch_interp2_sweep<T>(ns, Sweep2Points<T>{xs_.p, ys_.p, ix, items_.p, nitems_}, geom,
+                                nc, coef.data(), c, fw, opts.stream);
   else if (dim == 1)
     e = launch_spreadinterp<T, 1>(false, ns, pts, geom, nc, coef.data(), nullptr, c, fwm, opts.stream);
   else if (dim == 2)
@@ -445,6 +487,10 @@ template<class T> void Engine<T>::run_interp(C *c, const C *fw) {
   if (e == cudaErrorInvalidConfiguration) throw Failure{ERR_INSUFFICIENT_SHMEM};
   CU(e);
   ++launches;
+  if (staged_) {
+    launch_stage_out<C>(mid_.p, perm2_.p, cuser, (uint32_t)M, opts.stream);
+    ++launches;
+  }
 }
 
 // NU strengths -> modes: spread, FFT, deconvolve (include/finufft/execute.hpp:376-417, type 1)

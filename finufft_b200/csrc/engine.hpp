@@ -21,6 +21,7 @@
 #include "gridops.cuh"
 #include "sort.cuh"
 #include "spreadinterp.cuh"
+#include "stage.cuh"
 #include "sweep2d.cuh"
 
 namespace b200 {
@@ -37,6 +38,7 @@ struct EngineOpts {
   int allow_eps_too_small = 1;
   int sort_radix       = 0;     // 1: stable radix sort (reference permutation on the device)
   int sweep            = 1;     // 3D float: tube-sweep kernels (0 = generic kernels)
+  int stage            = -1;    // two-level strength permutation (stage.cuh): -1 auto, 0 off, 1 on
   int check_sigma      = 0;     // host (finufft_*) entry points apply the CPU feasibility rule
 };
 
@@ -97,7 +99,7 @@ template<class T> class Engine {
   void plan_grid();
   void sort_points(const T *x, const T *y, const T *z);
   bool use_sweep3(const void *grid) const;
-  cudaError_t sweep_run(bool spread, C *c, C *fw);
+  cudaError_t sweep_run(bool spread, C *c, C *fw, const uint32_t *ix);
   void build_sweep_items(uint32_t *scan_tmp);
   void run_spread(const C *c, C *fw);
   void run_interp(C *c, const C *fw);
@@ -122,6 +124,11 @@ template<class T> class Engine {
   uint32_t nitems_ = 0;
   bool swept_      = false;
   bool swept2_     = false;  // 2D sweep kernels (sweep2d.cuh) in use
+  // two-level permutation of the strengths (stage.cuh)
+  DevBuf<uint32_t> perm1_, perm2_;
+  DevBuf<C> mid_;
+  bool staged_ = false;
+  void build_staging();
   bool radix_order_ = false;  // sidx_ is the reference permutation as it stands
   // type 3
   DevBuf<T> xp_[3], sp_[3];

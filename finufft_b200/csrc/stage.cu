@@ -1,0 +1,128 @@
+// Two-level permutation of the strengths: see stage.cuh.
+#include "stage.cuh"
+
+#include "sort.cuh"
+
+namespace b200 {
+
+int stage_shift(uint64_t M, int elem_bytes) {
+  int shift = 25;  // 32 MB
+  for (int b = elem_bytes; b > 1; b >>= 1) --shift;
+  while (((M + (1ull << shift) - 1) >> shift) > (uint64_t)kStageMaxWindows) ++shift;
+  return shift;
+}
+
+// counts[w * nunits + u] = sorted positions of unit u whose user index lies in window w
+__global__ void __launch_bounds__(256)
+k_stage_count(const uint32_t *__restrict__ sidx, uint32_t M, int shift, uint32_t nunits,
+              uint32_t *__restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < nunits; u += nwarps) {
+    const uint32_t q0 = u * kStageUnit, q1 = min(M, q0 + kStageUnit);
+    uint32_t mine = 0;  // lane w counts window w
+    for (uint32_t q = q0 + lane; q < q0 + kStageUnit; q += 32) {
+      const uint32_t w = q < q1 ? sidx[q] >> shift : 0xffffffffu;
+#pragma unroll 1
+      for (uint32_t left = __activemask(); left;) {  // one ballot per distinct window
+        const uint32_t lead = __ffs(left) - 1;
+        const uint32_t wl   = __shfl_sync(0xffffffffu, w, lead);
+        const uint32_t same = __ballot_sync(0xffffffffu, w == wl);
+        if (wl != 0xffffffffu && (uint32_t)lane == wl) mine += __popc(same);
+        left &= ~same;
+      }
+    }
+    if (lane < kStageMaxWindows) counts[(size_t)lane * nunits + u] = mine;
+  }
+}
+
+// stable placement: slot of q = offsets[w * nunits + u] + number of earlier q of the unit in w
+__global__ void __launch_bounds__(256)
+k_stage_place(const uint32_t *__restrict__ sidx, uint32_t M, int shift, uint32_t nunits,
+              const uint32_t *__restrict__ offsets, uint32_t *__restrict__ perm1,
+              uint32_t *__restrict__ perm2) {
+  const int lane           = threadIdx.x & 31;
+  const uint32_t lt_mask   = (1u << lane) - 1u;
+  const uint32_t nwarps    = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < nunits; u += nwarps) {
+    const uint32_t q0 = u * kStageUnit, q1 = min(M, q0 + kStageUnit);
+    uint32_t run = lane < kStageMaxWindows ? offsets[(size_t)lane * nunits + u] : 0u;
+    for (uint32_t q = q0 + lane; q < q0 + kStageUnit; q += 32) {
+      const bool valid = q < q1;
+      const uint32_t j = valid ? sidx[q] : 0u;
+      const uint32_t w = valid ? j >> shift : 0xffffffffu;
+      const uint32_t peers = __match_any_sync(0xffffffffu, w);
+      const uint32_t base  = __shfl_sync(0xffffffffu, run, valid ? w : 0);
+      if (valid) {
+        const uint32_t m = base + __popc(peers & lt_mask);
+        perm1[q] = m;
+        perm2[m] = j;
+      }
+      // lane w advances its cursor by the size of window w's group
+      uint32_t add = 0;
+#pragma unroll 1
+      for (uint32_t left = __ballot_sync(0xffffffffu, valid); left;) {
+        const uint32_t lead = __ffs(left) - 1;
+        const uint32_t wl   = __shfl_sync(0xffffffffu, w, lead);
+        const uint32_t grp  = __shfl_sync(0xffffffffu, peers, lead);
+        if ((uint32_t)lane == wl) add = __popc(grp);
+        left &= ~grp;
+      }
+      run += add;
+    }
+  }
+}
+
+static inline int stage_grid(uint32_t nunits) {
+  const uint32_t want = (nunits + 7) / 8;
+  return (int)(want < 1 ? 1 : (want > 148u * 8 ? 148u * 8 : want));
+}
+
+void build_stage_perms(const uint32_t *sidx, uint32_t M, int shift, uint32_t *counts,
+                       uint32_t *offsets, uint32_t *scan_tmp, uint32_t *perm1, uint32_t *perm2,
+                       cudaStream_t st) {
+  if (M == 0) return;
+  const uint32_t nunits = (M + kStageUnit - 1) / kStageUnit;
+  k_stage_count<<<stage_grid(nunits), 256, 0, st>>>(sidx, M, shift, nunits, counts);
+  exclusive_scan_u32(counts, offsets, (uint32_t)kStageMaxWindows * nunits, scan_tmp, st);
+  k_stage_place<<<stage_grid(nunits), 256, 0, st>>>(sidx, M, shift, nunits, offsets, perm1, perm2);
+}
+
+template<class C>
+__global__ void __launch_bounds__(256)
+k_stage_in(const C *__restrict__ c, const uint32_t *__restrict__ perm2, C *__restrict__ mid,
+           uint32_t M) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += stride)
+    mid[m] = __ldg(c + __ldcs(perm2 + m));
+}
+template<class C>
+__global__ void __launch_bounds__(256)
+k_stage_out(const C *__restrict__ mid, const uint32_t *__restrict__ perm2, C *__restrict__ c,
+            uint32_t M) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += stride)
+    c[__ldcs(perm2 + m)] = __ldcs(mid + m);
+}
+static inline int stream_grid(uint32_t n) {
+  const uint32_t want = (n + 255) / 256;
+  return (int)(want < 1 ? 1 : (want > 148u * 16 ? 148u * 16 : want));
+}
+template<class C>
+void launch_stage_in(const C *c, const uint32_t *perm2, C *mid, uint32_t M, cudaStream_t st) {
+  if (M) k_stage_in<C><<<stream_grid(M), 256, 0, st>>>(c, perm2, mid, M);
+}
+template<class C>
+void launch_stage_out(const C *mid, const uint32_t *perm2, C *c, uint32_t M, cudaStream_t st) {
+  if (M) k_stage_out<C><<<stream_grid(M), 256, 0, st>>>(mid, perm2, c, M);
+}
+template void launch_stage_in<float2>(const float2 *, const uint32_t *, float2 *, uint32_t,
+                                      cudaStream_t);
+template void launch_stage_in<double2>(const double2 *, const uint32_t *, double2 *, uint32_t,
+                                       cudaStream_t);
+template void launch_stage_out<float2>(const float2 *, const uint32_t *, float2 *, uint32_t,
+                                       cudaStream_t);
+template void launch_stage_out<double2>(const double2 *, const uint32_t *, double2 *, uint32_t,
+                                        cudaStream_t);
+
+}  // namespace b200

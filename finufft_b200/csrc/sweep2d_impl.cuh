@@ -154,35 +154,61 @@ k_sweep2(const Sweep2Args<T, NS> a) {
   constexpr int NONE = INT_MIN;
   int jw = NONE;  // first column of the window; NONE = window empty
 
-  // spread: add this lane's column to the fine grid and clear it
+  // spread: add this lane's column to the fine grid and clear it.  Every lane group flushes its
+  // own copy (summing the copies with shuffles first was measured slower: the reductions hit
+  // the L2-resident grid and are cheaper than 4*YR shuffles per window move).
   auto flush_col = [&](int col) {
     const uint32_t gx = (uint32_t)wrap_index(col, nf1);
 #pragma unroll
     for (int r = 0; r < CF::YR; ++r) {
       const int gy = wrap_index(y0 + r, nf2);
-      const C v = acc[r];
+      const C v    = acc[r];
       if (v.x != (T)0 || v.y != (T)0)
         atomic_add_cx(a.fw + ((uint32_t)gy * (uint32_t)nf1 + gx), v);
       acc[r] = C{0, 0};
     }
   };
-  // interp: load this lane's column from the fine grid
-  auto load_col = [&](int col) {
-    const uint32_t gx = (uint32_t)wrap_index(col, nf1);
+  // interp: columns enter from the fine grid.  The owners of the columns that enter at the NEXT
+  // window move load them one move ahead into nxt[] (tag nxt_col), so the latency of the
+  // fine-grid reads is covered by a whole window position of work.
+  C nxt[SPREAD ? 1 : CF::YR];
+  int nxt_col = NONE;
+  auto fetch_col = [&](int col, C (&dst)[SPREAD ? 1 : CF::YR]) {
+    if constexpr (!SPREAD) {
+      const uint32_t gx = (uint32_t)wrap_index(col, nf1);
 #pragma unroll
-    for (int r = 0; r < CF::YR; ++r) {
-      const int gy = wrap_index(y0 + r, nf2);
-      acc[r] = __ldg(a.fw + ((uint32_t)gy * (uint32_t)nf1 + gx));
+      for (int r = 0; r < CF::YR; ++r) {
+        const int gy = wrap_index(y0 + r, nf2);
+        dst[r]       = __ldg(a.fw + ((uint32_t)gy * (uint32_t)nf1 + gx));
+      }
     }
   };
   // the window moves by S columns: [jw, jw+W) -> [jw+S, jw+S+W)
   auto slide = [&]() {
     const int rel = (la - jw) & (CF::W - 1);  // this lane's column is jw + rel
-    if (rel < CF::S) {
-      if (SPREAD) flush_col(jw + rel);
-      else load_col(jw + CF::W + rel);
+    if constexpr (SPREAD) {
+      if (rel < CF::S) flush_col(jw + rel);
+      jw += CF::S;
+    } else {
+      if (rel < CF::S) {
+        const int col = jw + CF::W + rel;
+        if (nxt_col == col) {
+#pragma unroll
+          for (int r = 0; r < CF::YR; ++r) acc[r] = nxt[r];
+        } else {
+          C tmp[CF::YR];
+          fetch_col(col, tmp);
+#pragma unroll
+          for (int r = 0; r < CF::YR; ++r) acc[r] = tmp[r];
+        }
+      }
+      jw += CF::S;
+      const int rn = (la - jw) & (CF::W - 1);
+      if (rn < CF::S) {
+        nxt_col = jw + CF::W + rn;
+        fetch_col(nxt_col, nxt);
+      }
     }
-    jw += CF::S;
   };
   auto empty_window = [&]() {
     if (jw == NONE) return;
@@ -211,7 +237,7 @@ k_sweep2(const Sweep2Args<T, NS> a) {
   };
   auto load_c = [&](uint32_t q, const Raw &r) {
     C c{0, 0};
-    if (SPREAD && q < item.qb) c = __ldcs(a.c_in + r.j);
+    if (SPREAD && q < item.qb) c = __ldg(a.c_in + r.j);
     return c;
   };
   Raw r1 = load_raw(item.qa + lane);

@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
   };
   auto load_c = [&](uint32_t q, const RawPoint &r) {
     float2 c = make_float2(0.f, 0.f);
-    if (SPREAD && q < item.qb && !(a.dbg & 4)) c = __ldcs(a.c_in + r.j);
+    if (SPREAD && q < item.qb && !(a.dbg & 4)) c = __ldg(a.c_in + r.j);
     return c;
   };
   RawPoint r1 = load_raw(item.qa + lane);
