@@ -156,15 +156,14 @@ k_sweep2(const Sweep2Args<T, NS> a) {
 
   // spread: add this lane's column to the fine grid and clear it.  Every lane group flushes its
   // own copy (summing the copies with shuffles first was measured slower: the reductions hit
-  // the L2-resident grid and are cheaper than 4*YR shuffles per window move).
+  // the L2-resident grid and are cheaper than 4*YR shuffles per window move), zeros included:
+  // testing for them costs a branch per row.
   auto flush_col = [&](int col) {
     const uint32_t gx = (uint32_t)wrap_index(col, nf1);
 #pragma unroll
     for (int r = 0; r < CF::YR; ++r) {
       const int gy = wrap_index(y0 + r, nf2);
-      const C v    = acc[r];
-      if (v.x != (T)0 || v.y != (T)0)
-        atomic_add_cx(a.fw + ((uint32_t)gy * (uint32_t)nf1 + gx), v);
+      atomic_add_cx(a.fw + ((uint32_t)gy * (uint32_t)nf1 + gx), acc[r]);
       acc[r] = C{0, 0};
     }
   };
