@@ -5,11 +5,14 @@
 // of reference include/finufft_common/safe_call.h:57-80.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
+#include <vector>
 
 #include "../../include/b200_cufinufft.h"
 #include "../../include/b200_finufft.h"
@@ -45,12 +48,38 @@ template<class T> struct HostPlan : DevicePlan<T> {
   DevBuf<T> x, y, z, s, t, u;
   DevBuf<C> c, fk;
   int64_t M = 0, N = 0;
+  // pipelined execute: copy streams for the two directions and events per unit of user data
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev;
   HostPlan(int type, int dim, const int64_t *nm, int iflag, int ntr, double tol,
            const EngineOpts &o)
       : DevicePlan<T>(type, dim, nm, iflag, ntr, tol, o) {
     this->host_api = true;
   }
+  ~HostPlan() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
+  }
+  cudaEvent_t event(size_t i) {
+    while (ev.size() <= i) {
+      cudaEvent_t e;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess)
+        throw Failure{ERR_CUDA_FAILURE};
+      ev.push_back(e);
+    }
+    return ev[i];
+  }
 };
+
+// Point groups of a host-pointer plan (engine.hpp set_point_groups): with one transform vector
+// of at least 64 MB, 4 groups let the spread of group k overlap the upload of group k+1 (and
+// the download of group k overlap the interpolation of k+1).  B200_NUFFT_HOST_GROUPS overrides.
+template<class T> int host_point_groups(int64_t M, int ntr, int type) {
+  if (const char *env = getenv("B200_NUFFT_HOST_GROUPS")) return std::max(1, atoi(env));
+  if (type == 3 || ntr > 1) return 1;  // many vectors pipeline vector by vector instead
+  return (uint64_t)M * sizeof(typename CxOf<T>::type) >= (64ull << 20) ? 4 : 1;
+}
 
 template<class F> int guarded(F &&f) {
   try {
@@ -225,32 +254,106 @@ int host_setpts(void *plan, int64_t M, const T *x, const T *y, const T *z, int64
     }
     p->M = M;
     p->N = N;
+    p->eng.set_point_groups(host_point_groups<T>(M, p->eng.ntr, p->eng.type));
     p->eng.setpts(M, p->x.p, p->y.p, p->z.p, N, p->s.p, p->t.p, p->u.p);
   });
 }
+// Host-pointer execute.  Types 1 and 2 are pipelined: all uploads are queued on one copy stream
+// in the order the engine consumes them, all downloads on another, and the engine's hooks
+// (ExecHooks) tie them to the compute stream with events, so that PCIe transfers and kernels
+// overlap: vector by vector for ntransf > 1, point group by point group for one large vector.
 template<class T> int host_execute(void *plan, void *c, void *fk, bool adjoint) {
   using C = typename CxOf<T>::type;
   return guarded([&] {
     auto *p = as_host_plan<T>(plan);
     DeviceGuard guard(p->eng.opts.device);
     cudaStream_t st     = p->eng.stream();
+    const int ntr       = p->eng.ntr;
+    const int64_t M     = p->M;
     const int64_t nout  = p->eng.type == 3 ? p->N : p->eng.mode_count();
-    const size_t nc_tot = (size_t)p->M * p->eng.ntr, nk_tot = (size_t)nout * p->eng.ntr;
+    const size_t nc_tot = (size_t)M * ntr, nk_tot = (size_t)nout * ntr;
     p->c.alloc(nc_tot);
     p->fk.alloc(nk_tot);
     const bool c_is_input = (p->eng.type != 2) != adjoint;
-    if (c_is_input) {
-      if (nc_tot) check_cuda(cudaMemcpyAsync(p->c.p, c, sizeof(C) * nc_tot, cudaMemcpyHostToDevice, st));
-    } else {
-      if (nk_tot) check_cuda(cudaMemcpyAsync(p->fk.p, fk, sizeof(C) * nk_tot, cudaMemcpyHostToDevice, st));
+    C *hc = static_cast<C *>(c), *hfk = static_cast<C *>(fk);
+    if (p->eng.type == 3 || nc_tot == 0 || nk_tot == 0) {  // plain: upload, run, download
+      if (c_is_input) {
+        if (nc_tot) check_cuda(cudaMemcpyAsync(p->c.p, c, sizeof(C) * nc_tot, cudaMemcpyHostToDevice, st));
+      } else {
+        if (nk_tot) check_cuda(cudaMemcpyAsync(p->fk.p, fk, sizeof(C) * nk_tot, cudaMemcpyHostToDevice, st));
+      }
+      p->eng.execute(p->c.p, p->fk.p, adjoint);
+      if (c_is_input) {
+        if (nk_tot) check_cuda(cudaMemcpyAsync(fk, p->fk.p, sizeof(C) * nk_tot, cudaMemcpyDeviceToHost, st));
+      } else {
+        if (nc_tot) check_cuda(cudaMemcpyAsync(c, p->c.p, sizeof(C) * nc_tot, cudaMemcpyDeviceToHost, st));
+      }
+      check_cuda(cudaStreamSynchronize(st));
+      return;
     }
-    p->eng.execute(p->c.p, p->fk.p, adjoint);
+    if (!p->s_in) check_cuda(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+    if (!p->s_out) check_cuda(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    const int ngrp      = p->eng.point_groups();
+    const int64_t glen  = ngrp > 1 ? p->eng.group_len() : M;
+    const int batch     = p->eng.batch;
+    const int nbatches  = (ntr + batch - 1) / batch;
+    // event slots: [0] start, then one per point unit (v, k), then one per mode batch
+    auto ev_pts  = [&](int v, int k) { return p->event(1 + (size_t)v * ngrp + k); };
+    auto ev_mode = [&](int b) { return p->event(1 + (size_t)ntr * ngrp + b); };
+    auto pt_range = [&](int v, int k, int64_t &off, int64_t &cnt) {
+      const int64_t a = std::min<int64_t>(M, (int64_t)k * glen);
+      const int64_t e = ngrp > 1 ? std::min<int64_t>(M, (int64_t)(k + 1) * glen) : M;
+      off = (int64_t)v * M + a;
+      cnt = e - a;
+    };
+    // copies may not start before earlier work on the plan's stream (previous execute) is done
+    check_cuda(cudaEventRecord(p->event(0), st));
+    check_cuda(cudaStreamWaitEvent(p->s_in, p->event(0), 0));
+    ExecHooks hooks;
     if (c_is_input) {
-      if (nk_tot) check_cuda(cudaMemcpyAsync(fk, p->fk.p, sizeof(C) * nk_tot, cudaMemcpyDeviceToHost, st));
+      for (int v = 0; v < ntr; ++v)
+        for (int k = 0; k < ngrp; ++k) {
+          int64_t off, cnt;
+          pt_range(v, k, off, cnt);
+          if (cnt > 0)
+            check_cuda(cudaMemcpyAsync(p->c.p + off, hc + off, sizeof(C) * (size_t)cnt,
+                                       cudaMemcpyHostToDevice, p->s_in));
+          check_cuda(cudaEventRecord(ev_pts(v, k), p->s_in));
+        }
+      hooks.before_points = [&](int v, int k) {
+        check_cuda(cudaStreamWaitEvent(st, ev_pts(v, k), 0));
+      };
+      hooks.after_modes = [&](int b0, int nb) {
+        const int b = b0 / batch;
+        check_cuda(cudaEventRecord(ev_mode(b), st));
+        check_cuda(cudaStreamWaitEvent(p->s_out, ev_mode(b), 0));
+        check_cuda(cudaMemcpyAsync(hfk + (size_t)b0 * nout, p->fk.p + (size_t)b0 * nout,
+                                   sizeof(C) * (size_t)nb * nout, cudaMemcpyDeviceToHost, p->s_out));
+      };
     } else {
-      if (nc_tot) check_cuda(cudaMemcpyAsync(c, p->c.p, sizeof(C) * nc_tot, cudaMemcpyDeviceToHost, st));
+      for (int b = 0; b < nbatches; ++b) {
+        const int b0 = b * batch, nb = std::min(batch, ntr - b0);
+        check_cuda(cudaMemcpyAsync(p->fk.p + (size_t)b0 * nout, hfk + (size_t)b0 * nout,
+                                   sizeof(C) * (size_t)nb * nout, cudaMemcpyHostToDevice, p->s_in));
+        check_cuda(cudaEventRecord(ev_mode(b), p->s_in));
+      }
+      hooks.before_modes = [&](int b0, int) {
+        check_cuda(cudaStreamWaitEvent(st, ev_mode(b0 / batch), 0));
+      };
+      hooks.after_points = [&](int v, int k) {
+        int64_t off, cnt;
+        pt_range(v, k, off, cnt);
+        check_cuda(cudaEventRecord(ev_pts(v, k), st));
+        check_cuda(cudaStreamWaitEvent(p->s_out, ev_pts(v, k), 0));
+        if (cnt > 0)
+          check_cuda(cudaMemcpyAsync(hc + off, p->c.p + off, sizeof(C) * (size_t)cnt,
+                                     cudaMemcpyDeviceToHost, p->s_out));
+      };
     }
+    p->eng.execute(p->c.p, p->fk.p, adjoint, &hooks);
     check_cuda(cudaStreamSynchronize(st));
+    check_cuda(cudaStreamSynchronize(p->s_in));
+    check_cuda(cudaStreamSynchronize(p->s_out));
   });
 }
 template<class T> int host_destroy(void *plan) {

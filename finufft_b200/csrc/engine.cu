@@ -171,7 +171,7 @@ template<class T> void Engine<T>::plan_grid() {
     nbins *= (uint64_t)geom.nb[d];
   }
   if (nbins > 0x7fffffffull) throw Failure{ERR_NDATA_NOTVALID};
-  geom.nbins = (uint32_t)nbins;
+  geom.nbins = geom.nbins1 = (uint32_t)nbins;
   if (opts.spreadinterponly) return;
   if (type == 3) {  // spread grid only: the inner type-2 plan owns the FFT and the series
     fw_.alloc((size_t)total);
@@ -264,6 +264,14 @@ static void refine2_impl(int ns, const Packed4<T> *packed, T *xs, T *ys, uint32_
 template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z) {
   cudaStream_t st = opts.stream;
   const uint32_t m = (uint32_t)M;
+  // point groups (sort.cuh): group-major sort keys; needs the counting sort
+  {
+    uint32_t k = (uint32_t)want_groups_;
+    if (type == 3 || M < 2 * (int64_t)k || (uint64_t)geom.nbins1 * k > 0x7fffffffull) k = 1;
+    geom.nchunks   = k;
+    geom.chunk_len = k > 1 ? (uint32_t)((M + k - 1) / k) : 0xffffffffu;
+    geom.nbins     = geom.nbins1 * k;
+  }
   xs_.alloc(M);
   if (dim > 1) ys_.alloc(M);
   if (dim > 2) zs_.alloc(M);
@@ -275,7 +283,7 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
   swept_ = std::is_same<T, float>::value && dim == 3 && sweep3_supported(ns) && opts.sweep &&
            nf[0] % 2 == 0 && M > 0;
   swept2_ = dim == 2 && sweep2_supported<T>(ns) && opts.sweep && M > 0;
-  radix_order_ = opts.sort_radix != 0;
+  radix_order_ = opts.sort_radix != 0 && geom.nchunks == 1;
 
   if (!radix_order_) {
     // counting sort: bin counts (warp-aggregated atomics) -> scan -> placement -> gather
@@ -335,6 +343,11 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
                      st));
   CU(cudaStreamSynchronize(st));
   nsub = total;
+  group_sub_.assign(geom.nchunks + 1, 0);
+  group_sub_[geom.nchunks] = total;
+  for (uint32_t k = 1; k < geom.nchunks; ++k)
+    CU(cudaMemcpyAsync(&group_sub_[k], substart.p + (size_t)k * geom.nbins1, sizeof(uint32_t),
+                       cudaMemcpyDeviceToHost, st));
   sub_bin_.alloc(std::max<uint32_t>(nsub, 1));
   sub_off_.alloc(std::max<uint32_t>(nsub, 1));
   if (nsub)
@@ -351,7 +364,7 @@ template<class T> void Engine<T>::build_staging() {
   const uint64_t bytes = (uint64_t)M * sizeof(C);
   staged_ = opts.stage > 0;  // opt-in: measured slower than the direct access
   (void)bytes;
-  if (M == 0) staged_ = false;
+  if (M == 0 || geom.nchunks > 1) staged_ = false;
   if (!staged_) return;
   int shift = stage_shift((uint64_t)M, (int)sizeof(C));
   if (const char *env = getenv("B200_NUFFT_STAGE_SHIFT")) {  // tests: many windows at small M
@@ -371,14 +384,20 @@ template<class T> void Engine<T>::build_staging() {
 
 template<class T> void Engine<T>::build_sweep_items(uint32_t *scan_tmp) {
   cudaStream_t st = opts.stream;
-  const uint32_t nrows = (uint32_t)geom.nb[1] * (uint32_t)geom.nb[2];
+  const uint32_t nrows1 = (uint32_t)geom.nb[1] * (uint32_t)geom.nb[2];
+  const uint32_t nrows  = nrows1 * geom.nchunks;  // rows are group-major like the bins
   Scratch<uint32_t> nit(nrows, st), itstart((size_t)nrows + 1, st);
   const uint32_t maxpts = swept2_ ? sweep2_item_points() : kSweepItemPoints;
   launch_row_item_count(binstart_.p, nrows, (uint32_t)geom.nb[0], maxpts, nit.p, st);
   exclusive_scan_u32(nit.p, itstart.p, nrows, scan_tmp, st);
   uint32_t total = 0;
   CU(cudaMemcpyAsync(&total, itstart.p + nrows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  group_item_.assign(geom.nchunks + 1, 0);
+  for (uint32_t k = 1; k < geom.nchunks; ++k)
+    CU(cudaMemcpyAsync(&group_item_[k], itstart.p + (size_t)k * nrows1, sizeof(uint32_t),
+                       cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  group_item_[geom.nchunks] = total;
   nitems_ = total;
   items_.alloc(std::max<uint32_t>(total, 1));
   if (total)
@@ -428,15 +447,23 @@ static cudaError_t sweep_impl(bool, int, const SweepPoints &, const GridGeom<dou
   return cudaErrorInvalidValue;
 }
 template<class T>
-cudaError_t Engine<T>::sweep_run(bool spread, C *c, C *fw, const uint32_t *ix) {
+cudaError_t Engine<T>::sweep_run(bool spread, C *c, C *fw, const uint32_t *ix, uint32_t it0,
+                                 uint32_t nit) {
   SweepPoints sp{reinterpret_cast<const float *>(xs_.p), reinterpret_cast<const float *>(ys_.p),
-                 reinterpret_cast<const float *>(zs_.p), ix, items_.p, nitems_};
+                 reinterpret_cast<const float *>(zs_.p), ix, items_.p + it0, nit};
   return sweep_impl(spread, ns, sp, geom, nc, coef.data(), c, fw, opts.stream);
 }
-template<class T> void Engine<T>::run_spread(const C *c, C *fw) {
+// group = -1: all points; else the work items / subproblems of that point group only
+template<class T> void Engine<T>::run_spread(const C *c, C *fw, int group) {
   if (nsub == 0) return;
-  PointSet<T> pts{xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, sub_bin_.p, sub_off_.p, nsub,
-                  (uint32_t)opts.maxsub};
+  uint32_t s0 = 0, s1 = nsub, it0 = 0, it1 = nitems_;
+  if (group >= 0) {
+    s0 = group_sub_[group], s1 = group_sub_[group + 1];
+    if (swept_ || swept2_) it0 = group_item_[group], it1 = group_item_[group + 1];
+  }
+  if (s1 == s0) return;
+  PointSet<T> pts{xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, sub_bin_.p + s0, sub_off_.p + s0,
+                  s1 - s0, (uint32_t)opts.maxsub};
   cudaError_t e;
   const uint32_t *ix = sidx_.p;
   if (staged_) {  // strengths grouped by window of the user index; kernels then index mid
@@ -447,10 +474,10 @@ template<class T> void Engine<T>::run_spread(const C *c, C *fw) {
     pts.sidx = ix;
   }
   if (use_sweep3(fw))
-    e = sweep_run(true, const_cast<C *>(c), fw, ix);
+    e = sweep_run(true, const_cast<C *>(c), fw, ix, it0, it1 - it0);
   else if (swept2_)
-    e = launch_spread2_sweep<T>(ns, Sweep2Points<T>{xs_.p, ys_.p, ix, items_.p, nitems_}, geom,
-                                nc, coef.data(), c, fw, opts.stream);
+    e = launch_spread2_sweep<T>(ns, Sweep2Points<T>{xs_.p, ys_.p, ix, items_.p + it0, it1 - it0},
+                                geom, nc, coef.data(), c, fw, opts.stream);
   else if (dim == 1)
     e = launch_spreadinterp<T, 1>(true, ns, pts, geom, nc, coef.data(), c, nullptr, fw, opts.stream);
   else if (dim == 2)
@@ -461,10 +488,16 @@ template<class T> void Engine<T>::run_spread(const C *c, C *fw) {
   CU(e);
   ++launches;
 }
-template<class T> void Engine<T>::run_interp(C *c, const C *fw) {
+template<class T> void Engine<T>::run_interp(C *c, const C *fw, int group) {
   if (nsub == 0) return;
-  PointSet<T> pts{xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, sub_bin_.p, sub_off_.p, nsub,
-                  (uint32_t)opts.maxsub};
+  uint32_t s0 = 0, s1 = nsub, it0 = 0, it1 = nitems_;
+  if (group >= 0) {
+    s0 = group_sub_[group], s1 = group_sub_[group + 1];
+    if (swept_ || swept2_) it0 = group_item_[group], it1 = group_item_[group + 1];
+  }
+  if (s1 == s0) return;
+  PointSet<T> pts{xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, sub_bin_.p + s0, sub_off_.p + s0,
+                  s1 - s0, (uint32_t)opts.maxsub};
   cudaError_t e;
   C *fwm = const_cast<C *>(fw);
   C *cuser = c;
@@ -475,10 +508,10 @@ template<class T> void Engine<T>::run_interp(C *c, const C *fw) {
     pts.sidx = ix;
   }
   if (use_sweep3(fw))
-    e = sweep_run(false, c, fwm, ix);
+    e = sweep_run(false, c, fwm, ix, it0, it1 - it0);
   else if (swept2_)
-    e = launch_interp2_sweep<T>(ns, Sweep2Points<T>{xs_.p, ys_.p, ix, items_.p, nitems_}, geom,
-                                nc, coef.data(), c, fw, opts.stream);
+    e = launch_interp2_sweep<T>(ns, Sweep2Points<T>{xs_.p, ys_.p, ix, items_.p + it0, it1 - it0},
+                                geom, nc, coef.data(), c, fw, opts.stream);
   else if (dim == 1)
     e = launch_spreadinterp<T, 1>(false, ns, pts, geom, nc, coef.data(), nullptr, c, fwm, opts.stream);
   else if (dim == 2)
@@ -495,7 +528,8 @@ template<class T> void Engine<T>::run_interp(C *c, const C *fw) {
 }
 
 // NU strengths -> modes: spread, FFT, deconvolve (include/finufft/execute.hpp:376-417, type 1)
-template<class T> void Engine<T>::spread_path(C *c, C *fk, int fsign) {
+template<class T>
+void Engine<T>::spread_path(C *c, C *fk, int fsign, const ExecHooks *hooks) {
   cudaStream_t st    = opts.stream;
   const int64_t G    = grid_cells(), Nm = mode_count();
   ModeGeom<T> mg;
@@ -511,11 +545,24 @@ template<class T> void Engine<T>::spread_path(C *c, C *fk, int fsign) {
     order_[0] = 0, order_[1] = 1, order_[2] = 2;
     mark(0);
     CU(cudaMemsetAsync(grid, 0, sizeof(C) * (size_t)G * nb, st));
-    for (int i = 0; i < nb; ++i) run_spread(c + (int64_t)(b0 + i) * M, grid + (int64_t)i * G);
+    const int ngrp = (int)geom.nchunks;
+    for (int i = 0; i < nb; ++i) {
+      const C *cv = c + (int64_t)(b0 + i) * M;
+      C *gv       = grid + (int64_t)i * G;
+      if (ngrp == 1 && !hooks) {
+        run_spread(cv, gv);
+        continue;
+      }
+      for (int k = 0; k < ngrp; ++k) {  // group k's strengths may still be on their way
+        if (hooks && hooks->before_points) hooks->before_points(b0 + i, k);
+        run_spread(cv, gv, ngrp == 1 ? -1 : k);
+      }
+    }
     mark(1);
     if (opts.spreadinterponly) {
       mark(2);
       mark(3);
+      if (hooks && hooks->after_modes) hooks->after_modes(b0, nb);
       continue;
     }
     fft_exec(fft_, fw_.p, fsign);
@@ -523,12 +570,14 @@ template<class T> void Engine<T>::spread_path(C *c, C *fk, int fsign) {
     launch_grid_to_modes<T>(dim, nb, fw_.p, fk + (int64_t)b0 * Nm, mg, st);
     ++launches;
     mark(3);
+    if (hooks && hooks->after_modes) hooks->after_modes(b0, nb);
   }
   CU(cudaGetLastError());
 }
 
 // modes -> NU values: amplify + zero-pad, FFT, interpolate (type 2)
-template<class T> void Engine<T>::interp_path(C *c, C *fk, int fsign) {
+template<class T>
+void Engine<T>::interp_path(C *c, C *fk, int fsign, const ExecHooks *hooks) {
   cudaStream_t st    = opts.stream;
   const int64_t G    = grid_cells(), Nm = mode_count();
   ModeGeom<T> mg;
@@ -542,6 +591,7 @@ template<class T> void Engine<T>::interp_path(C *c, C *fk, int fsign) {
     const int nb  = std::min(batch, ntr - b0);
     const C *grid = fw_.p;
     order_[0] = 2, order_[1] = 1, order_[2] = 0;  // intervals: amplify, fft, interp
+    if (hooks && hooks->before_modes) hooks->before_modes(b0, nb);
     mark(0);
     if (opts.spreadinterponly) {
       grid = fk + (int64_t)b0 * Nm;
@@ -554,13 +604,26 @@ template<class T> void Engine<T>::interp_path(C *c, C *fk, int fsign) {
       fft_exec(fft_, fw_.p, fsign);
       mark(2);
     }
-    for (int i = 0; i < nb; ++i) run_interp(c + (int64_t)(b0 + i) * M, grid + (int64_t)i * G);
+    const int ngrp = (int)geom.nchunks;
+    for (int i = 0; i < nb; ++i) {
+      C *cv       = c + (int64_t)(b0 + i) * M;
+      const C *gv = grid + (int64_t)i * G;
+      if (ngrp == 1 && !hooks) {
+        run_interp(cv, gv);
+        continue;
+      }
+      for (int k = 0; k < ngrp; ++k) {  // group k's values can leave while k+1 is computed
+        run_interp(cv, gv, ngrp == 1 ? -1 : k);
+        if (hooks && hooks->after_points) hooks->after_points(b0 + i, k);
+      }
+    }
     mark(3);
   }
   CU(cudaGetLastError());
 }
 
-template<class T> void Engine<T>::execute(C *c, C *fk, bool adjoint) {
+template<class T>
+void Engine<T>::execute(C *c, C *fk, bool adjoint, const ExecHooks *hooks) {
   DeviceGuard guard(opts.device);
   if (type == 3) {
     exec_type3(c, fk, adjoint);
@@ -568,8 +631,8 @@ template<class T> void Engine<T>::execute(C *c, C *fk, bool adjoint) {
   }
   const bool spreading = (type == 1) != adjoint;
   const int fsign      = adjoint ? -sign : sign;
-  if (spreading) spread_path(c, fk, fsign);
-  else interp_path(c, fk, fsign);
+  if (spreading) spread_path(c, fk, fsign, hooks);
+  else interp_path(c, fk, fsign, hooks);
 }
 
 template<class T> void Engine<T>::copy_sort_to_host(uint32_t *out) const {

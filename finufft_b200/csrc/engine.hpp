@@ -13,6 +13,7 @@
 #include <cufft.h>
 #include <stdint.h>
 
+#include <functional>
 #include <memory>
 #include <vector>
 
@@ -42,6 +43,15 @@ struct EngineOpts {
   int check_sigma      = 0;     // host (finufft_*) entry points apply the CPU feasibility rule
 };
 
+// Callbacks of a pipelined execute (host-pointer plans, capi.cu): the engine announces when it
+// is about to consume / has just produced a unit of user data, so the caller can order its
+// host<->device copies against the plan's stream.  A point unit is (vector v, group k) with k
+// indexing the nchunks groups of consecutive user indices (k = 0 when the plan is not split).
+struct ExecHooks {
+  std::function<void(int v, int k)> before_points, after_points;
+  std::function<void(int b0, int nb)> before_modes, after_modes;
+};
+
 template<class T> struct DevBuf {
   T *p     = nullptr;
   size_t n = 0;
@@ -68,7 +78,11 @@ template<class T> class Engine {
   // all pointers are device pointers on opts.device
   void setpts(int64_t M, const T *x, const T *y, const T *z, int64_t N, const T *s, const T *t,
               const T *u);
-  void execute(C *c, C *fk, bool adjoint);
+  void execute(C *c, C *fk, bool adjoint, const ExecHooks *hooks = nullptr);
+  // split the next setpts into k groups of consecutive user indices (types 1 and 2 only)
+  void set_point_groups(int k) { want_groups_ = k < 1 ? 1 : (k > 16 ? 16 : k); }
+  int point_groups() const { return (int)geom.nchunks; }
+  int64_t group_len() const { return (int64_t)geom.chunk_len; }
 
   // ---- introspection (tests, benches) ----
   int type, dim, ntr, sign;
@@ -99,12 +113,13 @@ template<class T> class Engine {
   void plan_grid();
   void sort_points(const T *x, const T *y, const T *z);
   bool use_sweep3(const void *grid) const;
-  cudaError_t sweep_run(bool spread, C *c, C *fw, const uint32_t *ix);
+  cudaError_t sweep_run(bool spread, C *c, C *fw, const uint32_t *ix, uint32_t it0,
+                        uint32_t nit);
   void build_sweep_items(uint32_t *scan_tmp);
-  void run_spread(const C *c, C *fw);
-  void run_interp(C *c, const C *fw);
-  void spread_path(C *c, C *fk, int fsign);
-  void interp_path(C *c, C *fk, int fsign);
+  void run_spread(const C *c, C *fw, int group = -1);
+  void run_interp(C *c, const C *fw, int group = -1);
+  void spread_path(C *c, C *fk, int fsign, const ExecHooks *hooks);
+  void interp_path(C *c, C *fk, int fsign, const ExecHooks *hooks);
   void exec_type3(C *c, C *fk, bool adjoint);
   void setpts_type3(int64_t M, const T *x, const T *y, const T *z, int64_t N, const T *s,
                     const T *t, const T *u);
@@ -122,6 +137,8 @@ template<class T> class Engine {
   DevBuf<uint32_t> sidx_, binstart_, sub_bin_, sub_off_;
   DevBuf<SweepItem> items_;  // 3D float sweep kernels: work items, refined bin order in use
   uint32_t nitems_ = 0;
+  int want_groups_ = 1;
+  std::vector<uint32_t> group_item_, group_sub_;  // first work item / subproblem of every group
   bool swept_      = false;
   bool swept2_     = false;  // 2D sweep kernels (sweep2d.cuh) in use
   // two-level permutation of the strengths (stage.cuh)

@@ -21,7 +21,7 @@ __global__ void k_bin_keys(const T *__restrict__ x, const T *__restrict__ y,
     if (DIM > 2)
       key += (uint32_t)g.nb[0] * (uint32_t)g.nb[1] *
              (uint32_t)(int)mul_rn(fold_rescale<T>(z[i], g.nf_t[2]), (T)(1.0 / kBinZ));
-    keys[i] = key < g.nbins ? key : g.nbins - 1;  // only non-finite input can trip this
+    keys[i] = key < g.nbins1 ? key : g.nbins1 - 1;  // only non-finite input can trip this
   }
 }
 
@@ -344,7 +344,7 @@ __device__ __forceinline__ uint32_t bin_key(T x, T y, T z, const GridGeom<T> &g)
   if (DIM > 2)
     key += (uint32_t)g.nb[0] * (uint32_t)g.nb[1] *
            (uint32_t)(int)mul_rn(fold_rescale<T>(z, g.nf_t[2]), (T)(1.0 / kBinZ));
-  return key < g.nbins ? key : g.nbins - 1;  // only non-finite input can trip this
+  return key < g.nbins1 ? key : g.nbins1 - 1;  // only non-finite input can trip this
 }
 
 template<class T, int DIM>
@@ -364,7 +364,8 @@ k_bin_count(const T *__restrict__ x, const T *__restrict__ y, const T *__restric
       if (DIM > 1) py = y[i];
       if (DIM > 2) pz = z[i];
     }
-    const uint32_t key = valid ? bin_key<T, DIM>(px, py, pz, g) : 0xffffffffu;
+    uint32_t key = valid ? bin_key<T, DIM>(px, py, pz, g) : 0xffffffffu;
+    if (valid && g.nchunks > 1) key += (i / g.chunk_len) * g.nbins1;  // group-major (sort.cuh)
     // one atomic per distinct bin in the warp
     const uint32_t peers = __match_any_sync(0xffffffffu, key);
     const int leader     = __ffs(peers) - 1;
@@ -559,7 +560,7 @@ k_refine_bins2(const Packed4<T> *__restrict__ packed, T *__restrict__ xs, T *__r
   const uint32_t total  = *nchunks;
   for (uint32_t ch = blockIdx.x * WARPS + warp; ch < total; ch += nwarps) {
     const uint32_t bin = chunk_bin[ch], q0 = chunk_off[ch];
-    const int i1 = bin % g.nb[0], i2 = bin / g.nb[0];
+    const int i1 = bin % g.nb[0], i2 = (bin / g.nb[0]) % g.nb[1];
     const int n  = (int)min((uint32_t)kRefCap, binstart[bin + 1] - q0);
     const int gbase = (kBinX * i1 - HL + XB) >> SH;
 #pragma unroll

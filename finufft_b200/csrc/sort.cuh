@@ -19,7 +19,14 @@ template<class T> struct GridGeom {
   int nf[3];      // fine grid size per dim (1 for unused dims)
   T nf_t[3];      // the same, converted to T the way the CPU code does (T(N))
   int nb[3];      // bins per dim
-  uint32_t nbins; // total bins
+  uint32_t nbins; // sort bins in total = nbins1 * nchunks
+  // Host-pointer plans may split the points into nchunks groups of chunk_len consecutive USER
+  // indices (capi.cu: the strengths of group k arrive while group k-1 is being spread).  The
+  // sort key is then group-major: key = group * nbins1 + bin, every group a complete bin-sorted
+  // point set of its own; kernels recover the bin with a modulo.
+  uint32_t nbins1    = 0;  // bins of the grid = nb[0]*nb[1]*nb[2]
+  uint32_t nchunks   = 1;
+  uint32_t chunk_len = 0xffffffffu;
 };
 
 // --- launchers (defined in sort.cu) -------------------------------------------------------

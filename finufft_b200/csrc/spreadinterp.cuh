@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) k_spread(const SpreadArgs<T, NS> a) {
   const uint32_t bin = a.pts.sub_bin[s], p0 = a.pts.sub_off[s];
   const uint32_t pend = min(a.pts.binstart[bin + 1], p0 + a.pts.maxsub);
   const int b1 = bin % a.g.nb[0], b2 = (bin / a.g.nb[0]) % a.g.nb[1],
-            b3 = bin / (a.g.nb[0] * a.g.nb[1]);
+            b3 = (bin / (a.g.nb[0] * a.g.nb[1])) % a.g.nb[2];  // bins are group-major
   const int org1 = kBinX * b1 - NS / 2, org2 = kBinY * b2 - NS / 2, org3 = kBinZ * b3 - NS / 2;
 
   for (int i = lane; i < TL::CELLS; i += 32) tile[i] = C{0, 0};
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) k_interp(const SpreadArgs<T, NS> a) {
   const uint32_t bin = a.pts.sub_bin[s], p0 = a.pts.sub_off[s];
   const uint32_t pend = min(a.pts.binstart[bin + 1], p0 + a.pts.maxsub);
   const int b1 = bin % a.g.nb[0], b2 = (bin / a.g.nb[0]) % a.g.nb[1],
-            b3 = bin / (a.g.nb[0] * a.g.nb[1]);
+            b3 = (bin / (a.g.nb[0] * a.g.nb[1])) % a.g.nb[2];  // bins are group-major
   const int org1 = kBinX * b1 - NS / 2, org2 = kBinY * b2 - NS / 2, org3 = kBinZ * b3 - NS / 2;
 
   // fill the tile from the fine grid (periodic)

@@ -144,7 +144,7 @@ k_sweep2(const Sweep2Args<T, NS> a) {
 
   const int g = lane / CF::W, la = lane % CF::W;
   const SweepItem item = a.pts.items[it];
-  const int i2  = (int)item.row;
+  const int i2  = (int)(item.row % (uint32_t)a.g.nb[1]);  // rows are group-major (sort.cuh)
   const int nf1 = a.g.nf[0], nf2 = a.g.nf[1];
   const int y0  = wrap_index(kBinY * i2 - CF::HL, nf2);  // fine-grid row of window row 0
 

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
   const int la = lane >> 2, bq = lane & 3;
   const SweepItem item = a.items[blockIdx.x];
   const int nb2 = a.g.nb[1];
-  const int i2 = item.row % nb2, i3 = item.row / nb2;
+  const int i2 = item.row % nb2, i3 = (item.row / nb2) % a.g.nb[2];  // rows are group-major
   const int nf1 = a.g.nf[0], nf2 = a.g.nf[1], nf3 = a.g.nf[2];
 
   // fine-grid offset of the (z, y) line each flush / fill iteration of this lane serves

@@ -332,6 +332,38 @@ def test_staged_strength_permutation(cuda, oracle, prec, tol, dim, modes, monkey
             assert np.array_equal(res["1"], res["0"])
 
 
+@pytest.mark.parametrize("groups", ["1", "3"])
+@pytest.mark.parametrize("prec,tol", [("f", 1e-5), ("d", 1e-10)])
+def test_host_api_pipelined_groups(cuda, oracle, prec, tol, groups, monkeypatch):
+    """finufft[f]_execute with host arrays: the pipelined path (copy streams + events, point
+    groups of consecutive user indices when B200_NUFFT_HOST_GROUPS > 1) gives the oracle's
+    numbers for types 1 and 2, one and several vectors, and the adjoint."""
+    import finufft_b200 as F
+    monkeypatch.setenv("B200_NUFFT_HOST_GROUPS", groups)
+    rng = np.random.default_rng(93)
+    rt, ct = _dt(prec)
+    for dim, modes in ((1, (400,)), (2, (48, 40)), (3, (20, 24, 18))):
+        M = 20_011
+        pts = make_points(rng, dim, M, rt, "wide")[:dim]
+        for type_, ntr in ((1, 1), (2, 1), (1, 3), (2, 3)):
+            hp = F.HostPlan(type_, modes, ntr, tol, 1, ct, upsampfac=2.0, allow_eps_too_small=1)
+            hp.setpts(*pts)
+            op = oracle.Plan(type_, list(modes[::-1]), 1, ntr, tol, rt, sigma=2.0,
+                             nthr=oracle.max_threads())
+            op.setpts(*(pts[::-1] + [None] * (3 - dim)))
+            shape = (M,) if type_ == 1 else modes
+            data = _rand_c(rng, ((ntr,) if ntr > 1 else ()) + shape, ct)
+            for rep in range(2):   # a second execute reuses streams and events
+                got = hp.execute(data)
+                assert oracle.relerr(got, op.execute(data)) <= 2 * tol, (dim, type_, ntr, rep)
+            if type_ == 1 and ntr == 1:
+                fk2 = _rand_c(rng, modes, ct)
+                cadj = hp.execute_adjoint(fk2)
+                lhs, rhs = np.vdot(fk2, got), np.vdot(cadj, data)
+                assert abs(lhs - rhs) <= (1e-4 if prec == "f" else 1e-9) * abs(lhs)
+            hp.destroy()
+
+
 def test_many_points_in_one_bin(cuda, oracle):
     """Clustered input: every point in a few bins, so bins split into many subproblems."""
     import finufft_b200 as F
