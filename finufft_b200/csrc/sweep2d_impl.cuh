@@ -170,9 +170,11 @@ k_sweep2(const Sweep2Args<T, NS> a) {
   // interp: columns enter from the fine grid.  The owners of the columns that enter at the NEXT
   // window move load them one move ahead into nxt[] (tag nxt_col), so the latency of the
   // fine-grid reads is covered by a whole window position of work.
-  C nxt[SPREAD ? 1 : CF::YR];
+  // (single precision only: in double the extra window column costs too many registers)
+  constexpr bool PREFETCH = !SPREAD && sizeof(T) == 4;
+  C nxt[PREFETCH ? CF::YR : 1];
   int nxt_col = NONE;
-  auto fetch_col = [&](int col, C (&dst)[SPREAD ? 1 : CF::YR]) {
+  auto fetch_col = [&](int col, auto &dst) {
     if constexpr (!SPREAD) {
       const uint32_t gx = (uint32_t)wrap_index(col, nf1);
 #pragma unroll
@@ -191,10 +193,15 @@ k_sweep2(const Sweep2Args<T, NS> a) {
     } else {
       if (rel < CF::S) {
         const int col = jw + CF::W + rel;
-        if (nxt_col == col) {
+        bool have = false;
+        if constexpr (PREFETCH) {
+          if (nxt_col == col) {
+            have = true;
 #pragma unroll
-          for (int r = 0; r < CF::YR; ++r) acc[r] = nxt[r];
-        } else {
+            for (int r = 0; r < CF::YR; ++r) acc[r] = nxt[r];
+          }
+        }
+        if (!have) {
           C tmp[CF::YR];
           fetch_col(col, tmp);
 #pragma unroll
@@ -202,10 +209,12 @@ k_sweep2(const Sweep2Args<T, NS> a) {
         }
       }
       jw += CF::S;
-      const int rn = (la - jw) & (CF::W - 1);
-      if (rn < CF::S) {
-        nxt_col = jw + CF::W + rn;
-        fetch_col(nxt_col, nxt);
+      if constexpr (PREFETCH) {
+        const int rn = (la - jw) & (CF::W - 1);
+        if (rn < CF::S) {
+          nxt_col = jw + CF::W + rn;
+          fetch_col(nxt_col, nxt);
+        }
       }
     }
   };
@@ -297,7 +306,8 @@ k_sweep2(const Sweep2Args<T, NS> a) {
       e                   = min(e, nc);
       advance_to(CF::S * kp - CF::XB);
       int q = p;
-      for (; q + 2 * CF::G <= e; q += 2 * CF::G) {  // two full steps: loads of both overlap
+      // float: two full steps at a time, loads of both first (double has no registers to spare)
+      for (; sizeof(T) == 4 && q + 2 * CF::G <= e; q += 2 * CF::G) {
         if constexpr (SPREAD) spread_step2x2<T, CF>(acc, sky, sxw, q + g, la);
         else interp_step2x2<T, CF>(acc, sky, sxw, spart, q + g, la);
       }
