@@ -306,8 +306,7 @@ k_sweep2(const Sweep2Args<T, NS> a) {
       e                   = min(e, nc);
       advance_to(CF::S * kp - CF::XB);
       int q = p;
-      // float: two full steps at a time, loads of both first (double has no registers to spare)
-      for (; sizeof(T) == 4 && q + 2 * CF::G <= e; q += 2 * CF::G) {
+      for (; q + 2 * CF::G <= e; q += 2 * CF::G) {  // two full steps: loads of both first
         if constexpr (SPREAD) spread_step2x2<T, CF>(acc, sky, sxw, q + g, la);
         else interp_step2x2<T, CF>(acc, sky, sxw, spart, q + g, la);
       }

@@ -62,8 +62,6 @@ __device__ __forceinline__ void eval_window2(const PairTable<NS> &tab, float x1,
   }
 }
 
-constexpr int kSweep3Occ = 16;  // default resident blocks per SM (see k_sweep3)
-
 template<int NS> struct SweepArgs {
   const float *xs, *ys, *zs;   // coordinates, refined bin order
   const uint32_t *sidx;        // position -> user index
@@ -161,10 +159,12 @@ __device__ __forceinline__ float2 interp_gather(
 // refined bin order keeps sorted by x window position.  SPREAD: accumulate into the register
 // window and reduce leaving rows into the fine grid; else: fill entering rows from the fine grid
 // and gather.
-// MINB = resident one-warp blocks per SM the register allocation aims at (16: 128 registers,
-// 20: 96 with a few spilled words, 24: 80); chosen by measurement, see launch_ns.
-template<int NS, bool SPREAD, int MINB>
-__global__ void __launch_bounds__(32, MINB) k_sweep3(const SweepArgs<NS> a) {
+// 16 resident one-warp blocks per SM (128 registers each).  Measured on B200 at C3: asking for
+// 20 blocks (96 registers, a few spilled words) takes 10.3 ms instead of 8.5, 24 blocks (80
+// registers) 13.6 ms: the kernel is bound by the FMA pipe, not by latency, so extra warps only
+// add spill traffic.
+template<int NS, bool SPREAD>
+__global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
   using CF = SweepCfg<NS>;
   extern __shared__ __align__(16) unsigned char smem[];
   float4 *stage4 = reinterpret_cast<float4 *>(smem);
@@ -423,9 +423,7 @@ static cudaError_t launch_ns(const SweepPoints &pts, const GridGeom<float> &g, i
   a.fw    = fw;
   a.dbg   = getenv("B200_SWEEP_DBG") ? atoi(getenv("B200_SWEEP_DBG")) : 0;
   const size_t shbytes = CF::STAGE_BYTES + CF::REC_BYTES + (SPREAD ? 0 : CF::PART_BYTES);
-  static const int occ = getenv("B200_SWEEP3_OCC") ? atoi(getenv("B200_SWEEP3_OCC")) : kSweep3Occ;
-  auto kern = occ >= 24 ? k_sweep3<NS, SPREAD, 24>
-                        : (occ >= 20 ? k_sweep3<NS, SPREAD, 20> : k_sweep3<NS, SPREAD, 16>);
+  auto kern            = k_sweep3<NS, SPREAD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)shbytes);
   if (e != cudaSuccess) return e;

@@ -12,7 +12,7 @@ echo "pytest exit $?" >> $out/${tag}_pytest_gpu.log
 tail -3 $out/${tag}_pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 3 > $out/${tag}_bench_c3_t1.json 2> $out/${tag}_bench_c3_t1.err
 tail -c 1500 $out/${tag}_bench_c3_t1.json
-for w in c3_t2 c2_t2 c4_t1; do
+for w in c3_t2 c2_t2 c2_t1 c4_t1; do
   timeout 400 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu > $out/${tag}_bench_$w.json 2> $out/${tag}_bench_$w.err
 done
 for w in c3_t1 c3_t2; do
@@ -28,4 +28,10 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sw
   -o $out/${tag}_sweep_spread python tools/prof_run.py --workload c3_t1 --reps 2 > $out/${tag}_ncu_full_spread.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sweep3 -c 1 -f \
   -o $out/${tag}_sweep_interp python tools/prof_run.py --workload c3_t2 --reps 1 > $out/${tag}_ncu_full_interp.log 2>&1
+# the 2D sweep kernels (config C2)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sweep2 -c 1 -f \
+  -o $out/${tag}_sweep2_interp python tools/prof_run.py --workload c2_t2 --reps 1 > $out/${tag}_ncu_full_interp2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sweep2 -c 1 -f \
+  -o $out/${tag}_sweep2_spread python tools/prof_run.py --workload c2_t1 --reps 1 > $out/${tag}_ncu_full_spread2.log 2>&1
+timeout 400 python bench.py --workload c2_t1 --dist cluster --steps 5 --warmup 3 --no-cpu > $out/${tag}_bench_c2_t1_cluster.json 2> $out/${tag}_bench_c2_t1_cluster.err
 ls -la $out
