@@ -146,7 +146,13 @@ def cpu_run(type_, modes, M, tol, dtype, steps, warmup, dist):
     from oracle import oracle as O
     rt = np.float32 if dtype == "complex64" else np.float64
     dim = len(modes)
-    nthr = O.max_threads()
+    # every core this process may run on: torchrun exports OMP_NUM_THREADS=1, which would
+    # otherwise turn the "all host threads" baseline into a single-thread one
+    try:
+        nthr = len(os.sched_getaffinity(0))
+    except AttributeError:
+        nthr = os.cpu_count() or 1
+    nthr = max(nthr, O.max_threads())
     plan = O.Plan(type_, list(modes), 1, 1, tol, rt, sigma=2.0, nthr=nthr)
     pts = synth_points(dim, M, rt, 1234, dist, plan.nf) + [None] * (3 - dim)
     t0 = time.perf_counter()

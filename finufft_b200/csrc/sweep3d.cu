@@ -36,7 +36,8 @@ template<int NS> struct SweepCfg {
   //         row bq+4m  [32,33] strength (spread)
   static constexpr size_t STAGE_BYTES = (size_t)NRED * 32 * sizeof(float4);
   static constexpr size_t REC_BYTES   = (size_t)(CH + 2) * RECW * sizeof(float);
-  static constexpr size_t PART_BYTES  = (size_t)CH * 9 * sizeof(float2);  // interp partial sums
+  static constexpr int PP = 17;  // pitch of a point's 16 partial sums (odd: conflict-free rows)
+  static constexpr size_t PART_BYTES  = (size_t)CH * PP * sizeof(float2);  // interp partial sums
   static_assert(NS + 1 <= W, "two stencil starts must fit the window");
   static_assert(HL <= XB && NS <= 7 && RZ <= 3, "layout");
 };
@@ -350,13 +351,12 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
       if (SPREAD) r.c = *reinterpret_cast<const float2 *>(rp + 32);
       return r;
     };
-    // reduce the four z-group lanes of a window row and park the row's share of point p
+    // add lane pairs and park the 16 partial sums of point p (the rest of the reduction runs
+    // thread-per-point after the chunk: one shuffle stage fewer on the per-point critical path)
     auto put_part = [&](int p, float2 v) {
       v.x += __shfl_xor_sync(0xffffffffu, v.x, 1);
       v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);
-      v.x += __shfl_xor_sync(0xffffffffu, v.x, 2);
-      v.y += __shfl_xor_sync(0xffffffffu, v.y, 2);
-      if (bq == 0) part[p * 9 + la] = v;
+      if ((lane & 1) == 0) part[p * CF::PP + (lane >> 1)] = v;
     };
     int p      = 0;
     LaneRec nx = load(0);
@@ -389,14 +389,15 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
 #undef B200_RUN
     }
     __syncwarp();
-    if (!SPREAD && lane < nc) {  // lane = point: add the eight window-row shares, scatter
-      float2 s = part[lane * 9];
+    if (!SPREAD && lane < nc) {  // lane = point: add its 16 partial sums, scatter
+      float2 s = part[lane * CF::PP], s2 = part[lane * CF::PP + 1];
 #pragma unroll
-      for (int r = 1; r < 8; ++r) {
-        const float2 v = part[lane * 9 + r];
+      for (int r = 2; r < 16; r += 2) {
+        const float2 v = part[lane * CF::PP + r], w = part[lane * CF::PP + r + 1];
         s.x += v.x, s.y += v.y;
+        s2.x += w.x, s2.y += w.y;
       }
-      a.c_out[cur.j] = s;
+      a.c_out[cur.j] = float2{s.x + s2.x, s.y + s2.y};
     }
     __syncwarp();
   }
