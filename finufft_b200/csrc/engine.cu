@@ -228,6 +228,11 @@ static uint32_t sweep2_item_points() {
   const long v  = e ? atol(e) : 0;
   return v >= 32 ? (uint32_t)v : kSweep2ItemPoints;
 }
+static uint32_t sweep3_item_points() {
+  const char *e = getenv("B200_SWEEP3_ITEM");
+  const long v  = e ? atol(e) : 0;
+  return v >= 32 ? (uint32_t)v : kSweepItemPoints;
+}
 // refined order inside the bins for the sweep kernels; work units = 512-point chunks of bins
 static void refine_impl(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
                         uint32_t *sidx, const uint32_t *binstart, const GridGeom<float> &g,
@@ -387,7 +392,7 @@ template<class T> void Engine<T>::build_sweep_items(uint32_t *scan_tmp) {
   const uint32_t nrows1 = (uint32_t)geom.nb[1] * (uint32_t)geom.nb[2];
   const uint32_t nrows  = nrows1 * geom.nchunks;  // rows are group-major like the bins
   Scratch<uint32_t> nit(nrows, st), itstart((size_t)nrows + 1, st);
-  const uint32_t maxpts = swept2_ ? sweep2_item_points() : kSweepItemPoints;
+  const uint32_t maxpts = swept2_ ? sweep2_item_points() : sweep3_item_points();
   launch_row_item_count(binstart_.p, nrows, (uint32_t)geom.nb[0], maxpts, nit.p, st);
   exclusive_scan_u32(nit.p, itstart.p, nrows, scan_tmp, st);
   uint32_t total = 0;

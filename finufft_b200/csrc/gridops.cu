@@ -10,104 +10,144 @@
 // (src/cuda/execute.cu:82-84).
 #include "gridops.cuh"
 
+#include <algorithm>
+
 namespace b200 {
 
+// Both kernels walk rows (fixed y, z index) so that the index arithmetic and the y/z factors
+// are paid once per row and the x loop is a coalesced stream: block = kRowsPerBlock rows of one
+// x tile of kTileX cells; blockIdx.z = transform in the batch.
+constexpr int kRowsPerBlock = 8, kTileX = 2048, kGridThreads = 256;
+
+// mode index (0..ms-1 in storage order) -> signed frequency k
+__device__ __forceinline__ int mode_freq(int pos, int ms, int modeord) {
+  const int kmin = -(ms / 2), kmax = (ms - 1) / 2;
+  return modeord == 0 ? pos + kmin : (pos <= kmax ? pos : pos - ms);
+}
+// fine-grid cell -> signed frequency, false if the cell is outside the kept band
+__device__ __forceinline__ bool cell_freq(int cell, int ms, int nf, int &k) {
+  const int kmin = -(ms / 2), kmax = (ms - 1) / 2;
+  if (cell <= kmax) k = cell;
+  else if (cell >= nf + kmin) k = cell - nf;
+  else return false;
+  return true;
+}
+__device__ __forceinline__ int mode_pos(int k, int ms, int modeord) {
+  return modeord == 0 ? k + ms / 2 : (k >= 0 ? k : ms + k);
+}
+
 template<class T, int DIM>
-__global__ void k_grid_to_modes(const typename CxOf<T>::type *__restrict__ fw,
-                                typename CxOf<T>::type *__restrict__ fk, ModeGeom<T> g) {
+__global__ void __launch_bounds__(kGridThreads)
+k_grid_to_modes(const typename CxOf<T>::type *__restrict__ fw,
+                typename CxOf<T>::type *__restrict__ fk, ModeGeom<T> g) {
   using C = typename CxOf<T>::type;
   const int64_t nm = (int64_t)g.ms[0] * g.ms[1] * g.ms[2];
   const int64_t ng = (int64_t)g.nf[0] * g.nf[1] * g.nf[2];
-  const C *fwb     = fw + (int64_t)blockIdx.y * ng;
-  C *fkb           = fk + (int64_t)blockIdx.y * nm;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < nm; m += stride) {
-    int pos[3] = {(int)(m % g.ms[0]), (int)((m / g.ms[0]) % g.ms[1]),
-                  (int)(m / ((int64_t)g.ms[0] * g.ms[1]))};
-    int64_t src = 0, pitch = 1;
-    int ak[3] = {0, 0, 0};
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      const int kmin = -(g.ms[d] / 2), kmax = (g.ms[d] - 1) / 2;
-      const int k = g.modeord == 0 ? pos[d] + kmin : (pos[d] <= kmax ? pos[d] : pos[d] - g.ms[d]);
-      src += pitch * (k >= 0 ? k : g.nf[d] + k);
-      pitch *= g.nf[d];
-      ak[d] = k >= 0 ? k : -k;
+  const C *fwb     = fw + (int64_t)blockIdx.z * ng;
+  C *fkb           = fk + (int64_t)blockIdx.z * nm;
+  const int nrows  = g.ms[1] * g.ms[2];
+  for (int x0 = blockIdx.y * kTileX; x0 < g.ms[0]; x0 += gridDim.y * kTileX) {
+    const int x1 = min(g.ms[0], x0 + kTileX);
+    for (int i = 0; i < kRowsPerBlock; ++i) {
+      const int row = blockIdx.x * kRowsPerBlock + i;
+      if (row >= nrows) break;
+      const int py = row % g.ms[1], pz = row / g.ms[1];
+      int64_t src = 0;
+      T p         = (T)1;
+      if (DIM > 2) {
+        const int k = mode_freq(pz, g.ms[2], g.modeord);
+        src += (int64_t)(k >= 0 ? k : g.nf[2] + k) * g.nf[1] * g.nf[0];
+        p = p / g.ph[2][k >= 0 ? k : -k];
+      }
+      if (DIM > 1) {
+        const int k = mode_freq(py, g.ms[1], g.modeord);
+        src += (int64_t)(k >= 0 ? k : g.nf[1] + k) * g.nf[0];
+        p = p / g.ph[1][k >= 0 ? k : -k];
+      }
+      const C *srow = fwb + src;
+      C *drow       = fkb + (int64_t)row * g.ms[0];
+      for (int px = x0 + threadIdx.x; px < x1; px += kGridThreads) {
+        const int k  = mode_freq(px, g.ms[0], g.modeord);
+        const T div  = g.ph[0][k >= 0 ? k : -k];
+        const C v    = srow[k >= 0 ? k : g.nf[0] + k];
+        drow[px]     = C{mul_rn(p, v.x) / div, mul_rn(p, v.y) / div};
+      }
     }
-    T p = (T)1;
-    if (DIM > 2) p = p / g.ph[2][ak[2]];
-    if (DIM > 1) p = p / g.ph[1][ak[1]];
-    const T div = g.ph[0][ak[0]];
-    const C v   = fwb[src];
-    fkb[m]      = C{mul_rn(p, v.x) / div, mul_rn(p, v.y) / div};
   }
 }
 
 template<class T, int DIM>
-__global__ void k_modes_to_grid(const typename CxOf<T>::type *__restrict__ fk,
-                                typename CxOf<T>::type *__restrict__ fw, ModeGeom<T> g) {
+__global__ void __launch_bounds__(kGridThreads)
+k_modes_to_grid(const typename CxOf<T>::type *__restrict__ fk,
+                typename CxOf<T>::type *__restrict__ fw, ModeGeom<T> g) {
   using C = typename CxOf<T>::type;
   const int64_t nm = (int64_t)g.ms[0] * g.ms[1] * g.ms[2];
   const int64_t ng = (int64_t)g.nf[0] * g.nf[1] * g.nf[2];
-  C *fwb           = fw + (int64_t)blockIdx.y * ng;
-  const C *fkb     = fk + (int64_t)blockIdx.y * nm;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ng; c += stride) {
-    int cell[3] = {(int)(c % g.nf[0]), (int)((c / g.nf[0]) % g.nf[1]),
-                   (int)(c / ((int64_t)g.nf[0] * g.nf[1]))};
-    int64_t src = 0, pitch = 1;
-    int ak[3] = {0, 0, 0};
-    bool inside = true;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      const int kmin = -(g.ms[d] / 2), kmax = (g.ms[d] - 1) / 2;
-      int k;
-      if (cell[d] <= kmax) k = cell[d];
-      else if (cell[d] >= g.nf[d] + kmin) k = cell[d] - g.nf[d];
-      else {
-        inside = false;
-        k      = 0;
+  C *fwb           = fw + (int64_t)blockIdx.z * ng;
+  const C *fkb     = fk + (int64_t)blockIdx.z * nm;
+  const int nrows  = g.nf[1] * g.nf[2];
+  for (int x0 = blockIdx.y * kTileX; x0 < g.nf[0]; x0 += gridDim.y * kTileX) {
+    const int x1 = min(g.nf[0], x0 + kTileX);
+    for (int i = 0; i < kRowsPerBlock; ++i) {
+      const int row = blockIdx.x * kRowsPerBlock + i;
+      if (row >= nrows) break;
+      const int cy = row % g.nf[1], cz = row / g.nf[1];
+      bool inside = true;
+      int64_t src = 0;
+      T p         = (T)1;
+      if (DIM > 2) {
+        int k = 0;
+        inside = cell_freq(cz, g.ms[2], g.nf[2], k) && inside;
+        src += (int64_t)mode_pos(k, g.ms[2], g.modeord) * g.ms[1] * g.ms[0];
+        p = p / g.ph[2][k >= 0 ? k : -k];
       }
-      src += pitch * (g.modeord == 0 ? k - kmin : (k >= 0 ? k : g.ms[d] + k));
-      pitch *= g.ms[d];
-      ak[d] = k >= 0 ? k : -k;
+      if (DIM > 1) {
+        int k = 0;
+        inside = cell_freq(cy, g.ms[1], g.nf[1], k) && inside;
+        src += (int64_t)mode_pos(k, g.ms[1], g.modeord) * g.ms[0];
+        p = p / g.ph[1][k >= 0 ? k : -k];
+      }
+      const C *srow = fkb + src;
+      C *drow       = fwb + (int64_t)row * g.nf[0];
+      for (int cx = x0 + threadIdx.x; cx < x1; cx += kGridThreads) {
+        C out = C{(T)0, (T)0};
+        int k = 0;
+        if (inside && cell_freq(cx, g.ms[0], g.nf[0], k)) {
+          const T div = g.ph[0][k >= 0 ? k : -k];
+          const C v   = srow[mode_pos(k, g.ms[0], g.modeord)];
+          out         = C{mul_rn(p, v.x) / div, mul_rn(p, v.y) / div};
+        }
+        drow[cx] = out;
+      }
     }
-    C out = C{(T)0, (T)0};
-    if (inside) {
-      T p = (T)1;
-      if (DIM > 2) p = p / g.ph[2][ak[2]];
-      if (DIM > 1) p = p / g.ph[1][ak[1]];
-      const T div = g.ph[0][ak[0]];
-      const C v   = fkb[src];
-      out         = C{mul_rn(p, v.x) / div, mul_rn(p, v.y) / div};
-    }
-    fwb[c] = out;
   }
+}
+
+template<class T>
+void launch_grid_to_modes(int dim, int batch, const typename CxOf<T>::type *fw,
+                          typename CxOf<T>::type *fk, const ModeGeom<T> &g, cudaStream_t st) {
+  const int nrows = g.ms[1] * g.ms[2];
+  dim3 grid((nrows + kRowsPerBlock - 1) / kRowsPerBlock,
+            std::min((g.ms[0] + kTileX - 1) / kTileX, 65535), batch);
+  if (dim == 1) k_grid_to_modes<T, 1><<<grid, kGridThreads, 0, st>>>(fw, fk, g);
+  else if (dim == 2) k_grid_to_modes<T, 2><<<grid, kGridThreads, 0, st>>>(fw, fk, g);
+  else k_grid_to_modes<T, 3><<<grid, kGridThreads, 0, st>>>(fw, fk, g);
+}
+template<class T>
+void launch_modes_to_grid(int dim, int batch, const typename CxOf<T>::type *fk,
+                          typename CxOf<T>::type *fw, const ModeGeom<T> &g, cudaStream_t st) {
+  const int nrows = g.nf[1] * g.nf[2];
+  dim3 grid((nrows + kRowsPerBlock - 1) / kRowsPerBlock,
+            std::min((g.nf[0] + kTileX - 1) / kTileX, 65535), batch);
+  if (dim == 1) k_modes_to_grid<T, 1><<<grid, kGridThreads, 0, st>>>(fk, fw, g);
+  else if (dim == 2) k_modes_to_grid<T, 2><<<grid, kGridThreads, 0, st>>>(fk, fw, g);
+  else k_modes_to_grid<T, 3><<<grid, kGridThreads, 0, st>>>(fk, fw, g);
 }
 
 static inline int blocks_for(int64_t n, int threads) {
   int64_t want = (n + threads - 1) / threads;
   const int64_t cap = 148 * 16;
   return (int)(want < 1 ? 1 : (want > cap ? cap : want));
-}
-
-template<class T>
-void launch_grid_to_modes(int dim, int batch, const typename CxOf<T>::type *fw,
-                          typename CxOf<T>::type *fk, const ModeGeom<T> &g, cudaStream_t st) {
-  const int64_t nm = (int64_t)g.ms[0] * g.ms[1] * g.ms[2];
-  dim3 grid(blocks_for(nm, 256), batch);
-  if (dim == 1) k_grid_to_modes<T, 1><<<grid, 256, 0, st>>>(fw, fk, g);
-  else if (dim == 2) k_grid_to_modes<T, 2><<<grid, 256, 0, st>>>(fw, fk, g);
-  else k_grid_to_modes<T, 3><<<grid, 256, 0, st>>>(fw, fk, g);
-}
-template<class T>
-void launch_modes_to_grid(int dim, int batch, const typename CxOf<T>::type *fk,
-                          typename CxOf<T>::type *fw, const ModeGeom<T> &g, cudaStream_t st) {
-  const int64_t ng = (int64_t)g.nf[0] * g.nf[1] * g.nf[2];
-  dim3 grid(blocks_for(ng, 256), batch);
-  if (dim == 1) k_modes_to_grid<T, 1><<<grid, 256, 0, st>>>(fk, fw, g);
-  else if (dim == 2) k_modes_to_grid<T, 2><<<grid, 256, 0, st>>>(fk, fw, g);
-  else k_modes_to_grid<T, 3><<<grid, 256, 0, st>>>(fk, fw, g);
 }
 
 // ---- type 3 element-wise helpers -----------------------------------------------------------

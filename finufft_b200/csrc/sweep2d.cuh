@@ -12,15 +12,17 @@
 //   * the x window of W (8 or 16) columns lives in the lanes: lane (g, a), a = lane % W, holds
 //     column x = a (mod W) with all YR rows in registers.  The 32/W lane groups g keep
 //     SEPARATE copies of the window and take different points, so one step of the inner loop
-//     handles 32/W points with ns packed FFMA2 (float) or 2*ns DFMA (double) per lane and no
+//     handles 32/W points with YR packed FFMA2 (float) or 2*YR DFMA (double) per lane and no
 //     cross-lane traffic;
-//   * setpts orders the points inside each bin by (x window position, y stencil start).  The
-//     y offset jb of a run is warp-uniform: a 5-way switch picks an unrolled body with static
-//     register indices;
-//   * when the window slides, the lanes owning the leaving columns add them to the fine grid
-//     with vector reductions (spread; every group flushes its own copy), or the lanes owning
-//     the entering columns load them (interp; the groups hold identical copies), and each
-//     point's value is reduced over the W lanes of its group with shuffles;
+//   * setpts orders the points inside each bin by (x window position, y stencil start).  A
+//     point's y window is stored zero-padded at the window rows it multiplies, so the inner
+//     loop does not depend on the y stencil start and a run is keyed by the window position
+//     alone; the run boundaries of a 32-point chunk come from one shfl_up + ballot;
+//   * when the window moves, the lanes owning the leaving columns add them to the fine grid
+//     with RED.64 (spread; every group flushes its own copy), or the lanes owning the entering
+//     columns install them (interp; the groups hold identical copies; in single precision
+//     they were loaded one window move ahead).  Interp: each lane parks its column's share
+//     of a point in shared memory and the chunk is summed thread-per-point afterwards;
 //   * point data is prepared thread-per-point, 32 points at a time: fold, stencil starts,
 //     Horner windows; the x window (times the strength for spread) is written rotated so that
 //     slot a belongs to column a (mod W).
@@ -52,7 +54,7 @@ template<class T> struct Sweep2Points {
   const SweepItem *items;
   uint32_t nitems;
 };
-constexpr uint32_t kSweep2ItemPoints = 4096;  // most points one warp takes
+constexpr uint32_t kSweep2ItemPoints = 2048;  // most points one warp takes (measured: 1024..4096 within 2 %)
 
 template<class T>
 cudaError_t launch_spread2_sweep(int ns, const Sweep2Points<T> &pts, const GridGeom<T> &g, int nc,

@@ -148,6 +148,8 @@ __device__ __forceinline__ float2 interp_gather(
   float2 tot = make_float2(0.f, 0.f);
 #pragma unroll
   for (int m = 0; m < CF::RZ; ++m) {
+    // one chain per row (splitting it in two was measured slower: the extra packed add per row
+    // costs more FMA-pipe time than the shorter dependency chain saves)
     float2 s = fmul2_s(ky[0], gv[m][JB]);
 #pragma unroll
     for (int t = 1; t < NS; ++t) s = ffma2_s(ky[t], gv[m][JB + t], s);
