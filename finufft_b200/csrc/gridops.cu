@@ -109,10 +109,20 @@ k_modes_to_grid(const typename CxOf<T>::type *__restrict__ fk,
       }
       const C *srow = fkb + src;
       C *drow       = fwb + (int64_t)row * g.nf[0];
+      if (!inside) {  // 1 - (ms/nf)^(dim-1) of the rows: plain zero fill, 16 bytes per store
+        if ((reinterpret_cast<uintptr_t>(drow + x0) & 15) == 0 && ((x1 - x0) * sizeof(C)) % 16 == 0) {
+          uint4 *d4   = reinterpret_cast<uint4 *>(drow + x0);
+          const int n = (int)((x1 - x0) * sizeof(C) / 16);
+          for (int q = threadIdx.x; q < n; q += kGridThreads) d4[q] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          for (int cx = x0 + threadIdx.x; cx < x1; cx += kGridThreads) drow[cx] = C{(T)0, (T)0};
+        }
+        continue;
+      }
       for (int cx = x0 + threadIdx.x; cx < x1; cx += kGridThreads) {
         C out = C{(T)0, (T)0};
         int k = 0;
-        if (inside && cell_freq(cx, g.ms[0], g.nf[0], k)) {
+        if (cell_freq(cx, g.ms[0], g.nf[0], k)) {
           const T div = g.ph[0][k >= 0 ? k : -k];
           const C v   = srow[mode_pos(k, g.ms[0], g.modeord)];
           out         = C{mul_rn(p, v.x) / div, mul_rn(p, v.y) / div};
