@@ -2,7 +2,7 @@
 """bench.py — headline benchmark of the finufft_b200 hot path (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--workload c3_t1|c3_t2|c2_t2|c2_t1|c4_t1] [--M pts] [--dist uniform|cluster]
+                  [--workload c3_t1|c3_t2|c2_t2|c2_t1|c4_t1|c1_t1] [--M pts] [--dist uniform|cluster]
 
 Workload (default c3_t1 = BASELINE.json configs[2], the config the metric is quoted on and
 that fits one GPU): 3D type 1, single precision, 256^3 modes (fine grid 512^3), M = 1e8
@@ -42,6 +42,8 @@ WORKLOADS = {
     "c2_t2": (2, (2048, 2048), 100_000_000, 1e-5, "complex64", 1),
     "c2_t1": (1, (2048, 2048), 100_000_000, 1e-5, "complex64", 1),
     "c4_t1": (1, (512, 512), 10_000_000, 1e-9, "complex128", 8),
+    # configs[0], the reference's own CPU-runnable case (perftest --prec d --type 1 --N1 1e6 --M 1e7)
+    "c1_t1": (1, (1_000_000,), 10_000_000, 1e-9, "complex128", 1),
 }
 # type 3 (configs[4]): M sources, N = M targets with frequencies of half-width 107.5 per dim
 # (perftest/perftest.cpp:197-202 with N1=N2=N3=215); benched by tools/bench_type3.py

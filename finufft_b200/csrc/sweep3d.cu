@@ -166,9 +166,9 @@ __device__ __forceinline__ float2 interp_gather(
 // 20 blocks (96 registers, a few spilled words) takes 10.3 ms instead of 8.5, 24 blocks (80
 // registers) 13.6 ms: the kernel is bound by the FMA pipe, not by latency, so extra warps only
 // add spill traffic.
-template<int NS, bool SPREAD, bool FULLP = false>
+template<int NS, bool SPREAD>
 __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
-  constexpr int PP = FULLP ? 33 : 17;  // pitch / number of partial sums per point (interp)
+  constexpr int PP = SweepCfg<NS>::PP;
   using CF = SweepCfg<NS>;
   extern __shared__ __align__(16) unsigned char smem[];
   float4 *stage4 = reinterpret_cast<float4 *>(smem);
@@ -354,16 +354,13 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
       if (SPREAD) r.c = *reinterpret_cast<const float2 *>(rp + 32);
       return r;
     };
-    // add lane pairs and park the 16 partial sums of point p (the rest of the reduction runs
-    // thread-per-point after the chunk: one shuffle stage fewer on the per-point critical path)
+    // add lane pairs and park the 16 partial sums of point p; the rest of the reduction runs
+    // thread-per-point after the chunk (10.58 -> 10.08 ms at C3 against two shuffle stages;
+    // parking all 32 partials with no shuffle at all measured the same as this)
     auto put_part = [&](int p, float2 v) {
-      if (FULLP) {
-        part[p * PP + lane] = v;
-      } else {
-        v.x += __shfl_xor_sync(0xffffffffu, v.x, 1);
-        v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);
-        if ((lane & 1) == 0) part[p * PP + (lane >> 1)] = v;
-      }
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, 1);
+      v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);
+      if ((lane & 1) == 0) part[p * PP + (lane >> 1)] = v;
     };
     int p      = 0;
     LaneRec nx = load(0);
@@ -430,11 +427,8 @@ static cudaError_t launch_ns(const SweepPoints &pts, const GridGeom<float> &g, i
   a.c_out = c_out;
   a.fw    = fw;
   a.dbg   = getenv("B200_SWEEP_DBG") ? atoi(getenv("B200_SWEEP_DBG")) : 0;
-  static const bool fullp = getenv("B200_SWEEP3_FULLP") && atoi(getenv("B200_SWEEP3_FULLP"));
-  const bool fp = fullp && !SPREAD;
-  const size_t shbytes = CF::STAGE_BYTES + CF::REC_BYTES +
-                         (SPREAD ? 0 : (fp ? (size_t)CF::CH * 33 * sizeof(float2) : CF::PART_BYTES));
-  auto kern = fp ? k_sweep3<NS, SPREAD, true> : k_sweep3<NS, SPREAD, false>;
+  const size_t shbytes = CF::STAGE_BYTES + CF::REC_BYTES + (SPREAD ? 0 : CF::PART_BYTES);
+  auto kern            = k_sweep3<NS, SPREAD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)shbytes);
   if (e != cudaSuccess) return e;

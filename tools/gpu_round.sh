@@ -12,7 +12,7 @@ echo "pytest exit $?" >> $out/${tag}_pytest_gpu.log
 tail -3 $out/${tag}_pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 3 > $out/${tag}_bench_c3_t1.json 2> $out/${tag}_bench_c3_t1.err
 tail -c 1500 $out/${tag}_bench_c3_t1.json
-for w in c3_t2 c2_t2 c2_t1 c4_t1; do
+for w in c3_t2 c2_t2 c2_t1 c4_t1 c1_t1; do
   timeout 400 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu > $out/${tag}_bench_$w.json 2> $out/${tag}_bench_$w.err
 done
 for w in c3_t1 c3_t2; do
