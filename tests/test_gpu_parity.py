@@ -364,6 +364,29 @@ def test_host_api_pipelined_groups(cuda, oracle, prec, tol, groups, monkeypatch)
             hp.destroy()
 
 
+def test_tiny_grids_wrap_inside_the_window(cuda, oracle):
+    """Fine grids narrower than the sweep kernels' lane window (nf = 2*ns < 8) and shorter than
+    their register rows: window columns / rows alias the same cells and must still add up."""
+    import finufft_b200 as F
+    rng = np.random.default_rng(97)
+    for prec, tols in (("f", (3e-1, 3e-3, 1e-5)), ("d", (3e-1, 3e-3, 1e-9))):
+        rt, ct = _dt(prec)
+        for modes in ((1, 1), (2, 3), (3, 1), (5, 2), (2, 2, 2), (1, 4, 3)):
+            dim, M = len(modes), 777
+            pts = make_points(rng, dim, M, rt, "wide")[:dim]
+            for tol in tols:
+                for type_ in (1, 2):
+                    gp, op = _plans(F, oracle, type_, modes, 1, tol, prec)
+                    gp.setpts(*[cuda.from_numpy(p).cuda() for p in pts])
+                    op.setpts(*(pts[::-1] + [None] * (3 - dim)))
+                    data = _rand_c(rng, (M,) if type_ == 1 else modes, ct)
+                    got = gp.execute(cuda.from_numpy(data).cuda()).cpu().numpy()
+                    want = op.execute(data)
+                    assert oracle.relerr(got, want) <= max(2 * tol, 5e-6 if prec == "f" else 1e-13), \
+                        (prec, modes, tol, type_)
+                    gp.destroy()
+
+
 def test_many_points_in_one_bin(cuda, oracle):
     """Clustered input: every point in a few bins, so bins split into many subproblems."""
     import finufft_b200 as F
