@@ -89,7 +89,6 @@ Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr
   if (const char *env = getenv("B200_NUFFT_SWEEP")) opts.sweep = atoi(env);  // debugging aids
   if (const char *env = getenv("B200_NUFFT_SORT")) opts.sort_radix = atoi(env) == 2;
   if (const char *env = getenv("B200_NUFFT_STAGE")) opts.stage = atoi(env);
-  if (const char *env = getenv("B200_SWEEP3_Q")) opts.sweepq = atoi(env);
   plan_kernel();
   if (type != 3) {
     for (int d = 0; d < dim; ++d) ms[d] = nmodes[d];
@@ -237,7 +236,7 @@ static uint32_t sweep3_item_points() {
 // refined order inside the bins for the sweep kernels; work units = 512-point chunks of bins
 static void refine_impl(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
                         uint32_t *sidx, const uint32_t *binstart, const GridGeom<float> &g,
-                        uint64_t M, uint32_t *scan_tmp, bool quad, cudaStream_t st) {
+                        uint64_t M, uint32_t *scan_tmp, cudaStream_t st) {
   const uint32_t max_chunks =
       (uint32_t)(M / kRefineChunk + std::min<uint64_t>(g.nbins, M));
   Scratch<uint32_t> nch(g.nbins, st), chstart((size_t)g.nbins + 1, st);
@@ -246,10 +245,10 @@ static void refine_impl(int ns, const Packed4<float> *packed, float *xs, float *
   exclusive_scan_u32(nch.p, chstart.p, g.nbins, scan_tmp, st);
   launch_sub_fill(binstart, chstart.p, g.nbins, kRefineChunk, chunk_bin.p, chunk_off.p, st);
   launch_refine_bins3(ns, packed, xs, ys, zs, sidx, binstart, chunk_bin.p, chunk_off.p,
-                      chstart.p + g.nbins, max_chunks, g, quad, st);
+                      chstart.p + g.nbins, max_chunks, g, st);
 }
 static void refine_impl(int, const Packed4<double> *, double *, double *, double *, uint32_t *,
-                        const uint32_t *, const GridGeom<double> &, uint64_t, uint32_t *, bool,
+                        const uint32_t *, const GridGeom<double> &, uint64_t, uint32_t *,
                         cudaStream_t) {}
 // the same for the 2D sweep kernels (any precision)
 template<class T>
@@ -289,7 +288,6 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
   swept_ = std::is_same<T, float>::value && dim == 3 && sweep3_supported(ns) && opts.sweep &&
            nf[0] % 2 == 0 && M > 0;
   swept2_ = dim == 2 && sweep2_supported<T>(ns) && opts.sweep && M > 0;
-  sweepq_ = swept_ && opts.sweepq != 0;
   radix_order_ = opts.sort_radix != 0 && geom.nchunks == 1;
 
   if (!radix_order_) {
@@ -302,7 +300,7 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
     launch_bin_place(keys.p, ranks.p, binstart_.p, m, sidx_.p, st);
     if (swept_)
       refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
-                  scan_tmp.p, sweepq_, st);
+                  scan_tmp.p, st);
     else if (swept2_)
       refine2_impl<T>(ns, packed.p, xs_.p, ys_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
                       scan_tmp.p, st);
@@ -329,7 +327,7 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
       launch_bin_count<T>(dim, x, y, z, m, geom, keys.p, ranks.p, cnt.p, packed.p, st);
       if (swept_)
         refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
-                    scan_tmp.p, sweepq_, st);
+                    scan_tmp.p, st);
       else
         refine2_impl<T>(ns, packed.p, xs_.p, ys_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
                         scan_tmp.p, st);
@@ -443,16 +441,13 @@ void Engine<T>::setpts(int64_t M_, const T *x, const T *y, const T *z, int64_t N
 template<class T> bool Engine<T>::use_sweep3(const void *grid) const {
   return swept_ && (reinterpret_cast<uintptr_t>(grid) & 15) == 0;
 }
-static cudaError_t sweep_impl(bool spread, bool quad, int ns, const SweepPoints &pts,
+static cudaError_t sweep_impl(bool spread, int ns, const SweepPoints &pts,
                               const GridGeom<float> &g, int nc, const float *coef, float2 *c,
                               float2 *fw, cudaStream_t st) {
-  if (quad)
-    return spread ? launch_spread3_sweepq(ns, pts, g, nc, coef, c, fw, st)
-                  : launch_interp3_sweepq(ns, pts, g, nc, coef, c, fw, st);
   return spread ? launch_spread3_sweep(ns, pts, g, nc, coef, c, fw, st)
                 : launch_interp3_sweep(ns, pts, g, nc, coef, c, fw, st);
 }
-static cudaError_t sweep_impl(bool, bool, int, const SweepPoints &, const GridGeom<double> &, int,
+static cudaError_t sweep_impl(bool, int, const SweepPoints &, const GridGeom<double> &, int,
                               const double *, double2 *, double2 *, cudaStream_t) {
   return cudaErrorInvalidValue;
 }
@@ -461,7 +456,7 @@ cudaError_t Engine<T>::sweep_run(bool spread, C *c, C *fw, const uint32_t *ix, u
                                  uint32_t nit) {
   SweepPoints sp{reinterpret_cast<const float *>(xs_.p), reinterpret_cast<const float *>(ys_.p),
                  reinterpret_cast<const float *>(zs_.p), ix, items_.p + it0, nit};
-  return sweep_impl(spread, sweepq_, ns, sp, geom, nc, coef.data(), c, fw, opts.stream);
+  return sweep_impl(spread, ns, sp, geom, nc, coef.data(), c, fw, opts.stream);
 }
 // group = -1: all points; else the work items / subproblems of that point group only
 template<class T> void Engine<T>::run_spread(const C *c, C *fw, int group) {

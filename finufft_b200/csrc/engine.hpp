@@ -39,7 +39,6 @@ struct EngineOpts {
   int allow_eps_too_small = 1;
   int sort_radix       = 0;     // 1: stable radix sort (reference permutation on the device)
   int sweep            = 1;     // 3D float: tube-sweep kernels (0 = generic kernels)
-  int sweepq           = 0;     // 3D float: quad-split sweep kernels (sweep3dq.cu)
   int stage            = -1;    // two-level strength permutation (stage.cuh): -1 auto, 0 off, 1 on
   int check_sigma      = 0;     // host (finufft_*) entry points apply the CPU feasibility rule
 };
@@ -141,8 +140,7 @@ template<class T> class Engine {
   int want_groups_ = 1;
   std::vector<uint32_t> group_item_, group_sub_;  // first work item / subproblem of every group
   bool swept_      = false;
-  bool swept2_     = false;
-  bool sweepq_     = false;  // the order was refined for the quad-split 3D kernels  // 2D sweep kernels (sweep2d.cuh) in use
+  bool swept2_     = false;  // 2D sweep kernels (sweep2d.cuh) in use
   // two-level permutation of the strengths (stage.cuh)
   DevBuf<uint32_t> perm1_, perm2_;
   DevBuf<C> mid_;

@@ -439,12 +439,10 @@ template void launch_gather_packed<double>(int, const Packed4<double> *, const u
 // memory in batches, bucketed by key = g*5 + jb (g: x window position inside the bin in steps
 // of two cells, jb: y stencil start inside the bin), ordered by index inside each bucket and
 // written out: coordinates to the sorted arrays, indices back to sidx.
-constexpr int kRefCap = 512, kRefWarps = 4, kRefKeys = 128;
+constexpr int kRefCap = 512, kRefWarps = 4, kRefKeys = 64;
 static_assert(kRefCap == (int)kRefineChunk, "chunk size");
 
-// QUAD: order for the quad-split kernels (sweep3dq.cu): key = g*9 + 3*(jb/2) + k0/2 with k0 the
-// z stencil start inside the bin.
-template<int NS, bool QUAD>
+template<int NS>
 __global__ void __launch_bounds__(kRefWarps * 32)
 k_refine_bins3(const Packed4<float> *__restrict__ packed, float *__restrict__ xs,
                float *__restrict__ ys, float *__restrict__ zs, uint32_t *__restrict__ sidx,
@@ -461,13 +459,11 @@ k_refine_bins3(const Packed4<float> *__restrict__ packed, float *__restrict__ xs
   const uint32_t total = *nchunks;
   for (uint32_t ch = blockIdx.x * kRefWarps + warp; ch < total; ch += nwarps) {
     const uint32_t bin = chunk_bin[ch], q0 = chunk_off[ch];
-    const int i1 = bin % g.nb[0], i2 = (bin / g.nb[0]) % g.nb[1],
-              i3 = (bin / (g.nb[0] * g.nb[1])) % g.nb[2];
+    const int i1 = bin % g.nb[0], i2 = (bin / g.nb[0]) % g.nb[1];
     {
       const int n = (int)min((uint32_t)kRefCap, binstart[bin + 1] - q0);
-#pragma unroll
-      for (int k = 0; k < kRefKeys / 32; ++k)
-        cnt[warp][lane + 32 * k] = 0, fill[warp][lane + 32 * k] = 0;
+      cnt[warp][lane] = 0, cnt[warp][lane + 32] = 0;
+      fill[warp][lane] = 0, fill[warp][lane + 32] = 0;
       __syncwarp();
       for (int k = lane; k < n; k += 32) {
         const uint32_t j        = sidx[q0 + k];
@@ -479,32 +475,22 @@ k_refine_bins3(const Packed4<float> *__restrict__ packed, float *__restrict__ xs
         stencil_start<float, NS>(fold_rescale<float>(pt.y, g.nf_t[1]), j0, t);
         const int gg  = min(max((i0 - (kBinX * i1 - XB)) >> 1, 0), NG - 1);
         const int jb  = min(max(j0 - (kBinY * i2 - HL), 0), kBinY);
-        int key       = gg * NJB + jb;
-        if (QUAD) {
-          int k0;
-          stencil_start<float, NS>(fold_rescale<float>(pt.z, g.nf_t[2]), k0, t);
-          k0  = min(max(k0 - (kBinZ * i3 - HL), 0), kBinZ);
-          key = gg * 9 + 3 * (jb >> 1) + (k0 >> 1);
-        }
+        const int key = gg * NJB + jb;
         skey[warp][k] = (uint16_t)key;
         atomicAdd(&cnt[warp][key], 1);
       }
       __syncwarp();
-      {  // exclusive scan of the counters, kRefKeys/32 per lane; cnt[kRefKeys] = n
-        constexpr int PL = kRefKeys / 32;
-        int v[PL], sum = 0;
-#pragma unroll
-        for (int k = 0; k < PL; ++k) v[k] = cnt[warp][PL * lane + k], sum += v[k];
-        int incl = sum;
+      {  // exclusive scan of the 64 counters, two per lane; cnt[64] = n
+        const int v0 = cnt[warp][2 * lane], v1 = cnt[warp][2 * lane + 1];
+        int incl = v0 + v1;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           const int up = __shfl_up_sync(0xffffffffu, incl, d);
           if (lane >= d) incl += up;
         }
         __syncwarp();
-        int run = incl - sum;
-#pragma unroll
-        for (int k = 0; k < PL; ++k) cnt[warp][PL * lane + k] = run, run += v[k];
+        cnt[warp][2 * lane]     = incl - v0 - v1;
+        cnt[warp][2 * lane + 1] = incl - v1;
         if (lane == 31) cnt[warp][kRefKeys] = incl;
       }
       __syncwarp();
@@ -532,20 +518,14 @@ k_refine_bins3(const Packed4<float> *__restrict__ packed, float *__restrict__ xs
 void launch_refine_bins3(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
                          uint32_t *sidx, const uint32_t *binstart, const uint32_t *chunk_bin,
                          const uint32_t *chunk_off, const uint32_t *nchunks, uint32_t max_chunks,
-                         const GridGeom<float> &g, bool quad, cudaStream_t st) {
+                         const GridGeom<float> &g, cudaStream_t st) {
   if (max_chunks == 0) return;
   const int nb = grid_for((max_chunks + kRefWarps - 1) / kRefWarps * 32 * kRefWarps, kRefWarps * 32, 16);
   switch (ns) {
 #define B200_REF(NSV)                                                                          \
   case NSV:                                                                                    \
-    if (quad)                                                                                  \
-      k_refine_bins3<NSV, true><<<nb, kRefWarps * 32, 0, st>>>(packed, xs, ys, zs, sidx,       \
-                                                               binstart, chunk_bin, chunk_off, \
-                                                               nchunks, g);                    \
-    else                                                                                       \
-      k_refine_bins3<NSV, false><<<nb, kRefWarps * 32, 0, st>>>(packed, xs, ys, zs, sidx,      \
-                                                                binstart, chunk_bin,           \
-                                                                chunk_off, nchunks, g);        \
+    k_refine_bins3<NSV><<<nb, kRefWarps * 32, 0, st>>>(packed, xs, ys, zs, sidx, binstart,     \
+                                                       chunk_bin, chunk_off, nchunks, g);      \
     break;
     B200_REF(2) B200_REF(3) B200_REF(4) B200_REF(5) B200_REF(6) B200_REF(7)
 #undef B200_REF
@@ -680,7 +660,7 @@ __global__ void k_row_item_count(const uint32_t *__restrict__ binstart, uint32_t
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
     const uint32_t n = binstart[(size_t)(r + 1) * nb1] - binstart[(size_t)r * nb1];
-    nitems[r]        = min((n + maxpts - 1) / maxpts, kMaxItemsPerRow);
+    nitems[r]        = (n + maxpts - 1) / maxpts;
   }
 }
 __global__ void k_row_item_fill(const uint32_t *__restrict__ binstart,
@@ -689,14 +669,8 @@ __global__ void k_row_item_fill(const uint32_t *__restrict__ binstart,
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
     const uint32_t qs = binstart[(size_t)r * nb1], qe = binstart[(size_t)(r + 1) * nb1];
-    const uint32_t n = qe - qs, cnt = min((n + maxpts - 1) / maxpts, kMaxItemsPerRow);
-    if (cnt == 0) continue;
-    const uint32_t len = (n + cnt - 1) / cnt;  // = maxpts unless the row hit the item cap
     uint32_t s = itemstart[r];
-    for (uint32_t k = 0; k < cnt; ++k, ++s) {
-      const uint32_t q = qs + min(n, k * len);
-      items[s] = SweepItem{r, q, qs + min(n, (k + 1) * len)};
-    }
+    for (uint32_t q = qs; q < qe; q += maxpts, ++s) items[s] = SweepItem{r, q, min(qe, q + maxpts)};
   }
 }
 void launch_row_item_count(const uint32_t *binstart, uint32_t nrows, uint32_t nb1,

@@ -96,17 +96,13 @@ constexpr uint32_t kRefineChunk = 512;
 void launch_refine_bins3(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
                          uint32_t *sidx, const uint32_t *binstart, const uint32_t *chunk_bin,
                          const uint32_t *chunk_off, const uint32_t *nchunks, uint32_t max_chunks,
-                         const GridGeom<float> &g, bool quad, cudaStream_t st);
+                         const GridGeom<float> &g, cudaStream_t st);
 
 // Work items of the sweep kernels: every row of bins (i2, i3) cut into runs of at most
 // `maxpts` consecutive points.  item = {row, first point, one past last point}.
 struct SweepItem {
   uint32_t row, qa, qb;
 };
-// A row holding a large share of all points (clustered input) is cut into at most this many
-// items: enough to fill the machine, while every further item would only add one more window
-// flush onto the same few fine-grid cells (same-address reductions serialise in the L2).
-constexpr uint32_t kMaxItemsPerRow = 2048;
 void launch_row_item_count(const uint32_t *binstart, uint32_t nrows, uint32_t nb1,
                            uint32_t maxpts, uint32_t *nitems, cudaStream_t st);
 void launch_row_item_fill(const uint32_t *binstart, const uint32_t *itemstart, uint32_t nrows,

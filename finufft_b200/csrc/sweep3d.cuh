@@ -63,12 +63,4 @@ cudaError_t launch_interp3_sweep(int ns, const SweepPoints &pts, const GridGeom<
                                  const float *coef, float2 *c_out, const float2 *fw,
                                  cudaStream_t st);
 
-// "quad split" register layout (sweep3dq.cu): wants the order refined with quad = true
-cudaError_t launch_spread3_sweepq(int ns, const SweepPoints &pts, const GridGeom<float> &g, int nc,
-                                  const float *coef, const float2 *c_in, float2 *fw,
-                                  cudaStream_t st);
-cudaError_t launch_interp3_sweepq(int ns, const SweepPoints &pts, const GridGeom<float> &g, int nc,
-                                  const float *coef, float2 *c_out, const float2 *fw,
-                                  cudaStream_t st);
-
 }  // namespace b200
