@@ -440,6 +440,7 @@ template void launch_gather_packed<double>(int, const Packed4<double> *, const u
 // of two cells, jb: y stencil start inside the bin), ordered by index inside each bucket and
 // written out: coordinates to the sorted arrays, indices back to sidx.
 constexpr int kRefCap = 512, kRefWarps = 4, kRefKeys = 64;
+constexpr int kRefBatch = 8;  // gathers a lane issues back to back
 static_assert(kRefCap == (int)kRefineChunk, "chunk size");
 
 template<int NS>
@@ -465,19 +466,35 @@ k_refine_bins3(const Packed4<float> *__restrict__ packed, float *__restrict__ xs
       cnt[warp][lane] = 0, cnt[warp][lane + 32] = 0;
       fill[warp][lane] = 0, fill[warp][lane + 32] = 0;
       __syncwarp();
-      for (int k = lane; k < n; k += 32) {
-        const uint32_t j        = sidx[q0 + k];
-        const Packed4<float> pt = packed[j];
-        sx[warp][k] = pt.x, sy[warp][k] = pt.y, sz[warp][k] = pt.z, si[warp][k] = j;
-        int i0, j0;
-        float t;
-        stencil_start<float, NS>(fold_rescale<float>(pt.x, g.nf_t[0]), i0, t);
-        stencil_start<float, NS>(fold_rescale<float>(pt.y, g.nf_t[1]), j0, t);
-        const int gg  = min(max((i0 - (kBinX * i1 - XB)) >> 1, 0), NG - 1);
-        const int jb  = min(max(j0 - (kBinY * i2 - HL), 0), kBinY);
-        const int key = gg * NJB + jb;
-        skey[warp][k] = (uint16_t)key;
-        atomicAdd(&cnt[warp][key], 1);
+      // the gathers are random 16-byte reads (a 128-byte line of HBM traffic each): issue
+      // kRefBatch of them per lane before touching the data, or the kernel is latency-bound
+      for (int kb = 0; kb < n; kb += 32 * kRefBatch) {
+        uint32_t jj[kRefBatch];
+        Packed4<float> pp[kRefBatch];
+#pragma unroll
+        for (int u = 0; u < kRefBatch; ++u) {
+          const int k = kb + 32 * u + lane;
+          jj[u]       = k < n ? sidx[q0 + k] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kRefBatch; ++u)
+          if (kb + 32 * u + lane < n) pp[u] = packed[jj[u]];
+#pragma unroll
+        for (int u = 0; u < kRefBatch; ++u) {
+          const int k = kb + 32 * u + lane;
+          if (k >= n) continue;
+          const Packed4<float> pt = pp[u];
+          sx[warp][k] = pt.x, sy[warp][k] = pt.y, sz[warp][k] = pt.z, si[warp][k] = jj[u];
+          int i0, j0;
+          float t;
+          stencil_start<float, NS>(fold_rescale<float>(pt.x, g.nf_t[0]), i0, t);
+          stencil_start<float, NS>(fold_rescale<float>(pt.y, g.nf_t[1]), j0, t);
+          const int gg  = min(max((i0 - (kBinX * i1 - XB)) >> 1, 0), NG - 1);
+          const int jb  = min(max(j0 - (kBinY * i2 - HL), 0), kBinY);
+          const int key = gg * NJB + jb;
+          skey[warp][k] = (uint16_t)key;
+          atomicAdd(&cnt[warp][key], 1);
+        }
       }
       __syncwarp();
       {  // exclusive scan of the 64 counters, two per lane; cnt[64] = n
@@ -566,19 +583,34 @@ k_refine_bins2(const Packed4<T> *__restrict__ packed, T *__restrict__ xs, T *__r
 #pragma unroll
     for (int k = 0; k < KEYS / 32; ++k) cnt[warp][lane + 32 * k] = 0, fill[warp][lane + 32 * k] = 0;
     __syncwarp();
-    for (int k = lane; k < n; k += 32) {
-      const uint32_t j    = sidx[q0 + k];
-      const Packed4<T> pt = packed[j];
-      sx[warp][k] = pt.x, sy[warp][k] = pt.y, si[warp][k] = j;
-      int i0, j0;
-      T t;
-      stencil_start<T, NS>(fold_rescale<T>(pt.x, g.nf_t[0]), i0, t);
-      stencil_start<T, NS>(fold_rescale<T>(pt.y, g.nf_t[1]), j0, t);
-      const int gg  = min(max(((i0 + XB) >> SH) - gbase, 0), NG - 1);
-      const int jb  = min(max(j0 - (kBinY * i2 - HL), 0), kBinY);
-      const int key = gg * NJB + jb;
-      skey[warp][k] = (uint16_t)key;
-      atomicAdd(&cnt[warp][key], 1);
+    constexpr int UB = sizeof(T) == 4 ? kRefBatch : kRefBatch / 2;  // gathers in flight per lane
+    for (int kb = 0; kb < n; kb += 32 * UB) {
+      uint32_t jj[UB];
+      Packed4<T> pp[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int k = kb + 32 * u + lane;
+        jj[u]       = k < n ? sidx[q0 + k] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u)
+        if (kb + 32 * u + lane < n) pp[u] = packed[jj[u]];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int k = kb + 32 * u + lane;
+        if (k >= n) continue;
+        const Packed4<T> pt = pp[u];
+        sx[warp][k] = pt.x, sy[warp][k] = pt.y, si[warp][k] = jj[u];
+        int i0, j0;
+        T t;
+        stencil_start<T, NS>(fold_rescale<T>(pt.x, g.nf_t[0]), i0, t);
+        stencil_start<T, NS>(fold_rescale<T>(pt.y, g.nf_t[1]), j0, t);
+        const int gg  = min(max(((i0 + XB) >> SH) - gbase, 0), NG - 1);
+        const int jb  = min(max(j0 - (kBinY * i2 - HL), 0), kBinY);
+        const int key = gg * NJB + jb;
+        skey[warp][k] = (uint16_t)key;
+        atomicAdd(&cnt[warp][key], 1);
+      }
     }
     __syncwarp();
     {  // exclusive scan of the KEYS counters, KEYS/32 per lane; cnt[KEYS] = n
