@@ -89,6 +89,7 @@ Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr
   if (const char *env = getenv("B200_NUFFT_SWEEP")) opts.sweep = atoi(env);  // debugging aids
   if (const char *env = getenv("B200_NUFFT_SORT")) opts.sort_radix = atoi(env) == 2;
   if (const char *env = getenv("B200_NUFFT_STAGE")) opts.stage = atoi(env);
+  if (const char *env = getenv("B200_NUFFT_PRUNE")) opts.prune = atoi(env);
   plan_kernel();
   if (type != 3) {
     for (int d = 0; d < dim; ++d) ms[d] = nmodes[d];
@@ -96,8 +97,39 @@ Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr
   }
 }
 
-template<class T> Engine<T>::~Engine() {
+template<class T> void Engine<T>::destroy_fft() {
   if (have_fft_) cufftDestroy(fft_);
+  have_fft_ = false;
+  if (pruned_) {
+    cufftDestroy(fftz_);
+    for (int r = 0; r < 2; ++r)
+      if (xy_count_[r]) cufftDestroy(fftxy_[r]);
+  }
+  pruned_      = false;
+  xy_count_[0] = xy_count_[1] = 0;
+}
+
+// In-place FFT of nb fine grids.  Pruned form (3D): for type 1 the z transform runs first and the
+// x,y transforms only on the planes whose kz is kept by the deconvolve step; for type 2 the x,y
+// transforms run first, only on the planes amplify filled (the others are zero and stay zero),
+// then z.  The reference's CPU path prunes the same way with DUCC0 (src/fft.cpp:299-362).
+template<class T> void Engine<T>::fft_grid(C *grid, int nb, int fsign, bool spreading) {
+  if (!pruned_) {
+    fft_exec(fft_, grid, fsign);
+    return;
+  }
+  const int64_t G = grid_cells(), plane = nf[0] * nf[1];
+  for (int i = 0; i < nb; ++i) {
+    C *g = grid + (int64_t)i * G;
+    if (spreading) fft_exec(fftz_, g, fsign);
+    for (int r = 0; r < 2; ++r)
+      if (xy_count_[r]) fft_exec(fftxy_[r], g + xy_first_[r] * plane, fsign);
+    if (!spreading) fft_exec(fftz_, g, fsign);
+  }
+}
+
+template<class T> Engine<T>::~Engine() {
+  destroy_fft();
   for (auto &e : ev_)
     if (e) cudaEventDestroy(e);
 }
@@ -195,12 +227,39 @@ template<class T> void Engine<T>::plan_grid() {
     CU(cudaStreamSynchronize(st));  // ph is a temporary
   }
   fw_.alloc((size_t)total * batch);
-  if (have_fft_) {
-    cufftDestroy(fft_);
-    have_fft_ = false;
-  }
+  destroy_fft();
   int n[3];
   for (int d = 0; d < dim; ++d) n[d] = (int)nf[dim - 1 - d];  // slowest first
+  // pruned form when at most 3/4 of the z-planes are needed (sigma = 2: half of them)
+  if (dim == 3 && opts.prune && 4 * ms[2] <= 3 * nf[2] && nf[0] * nf[1] > 1) {
+    const int plane = (int)(nf[0] * nf[1]);
+    int nz[1] = {(int)nf[2]}, emb[1] = {(int)nf[2]};
+    bool ok = cufftPlanMany(&fftz_, 1, nz, emb, plane, 1, emb, plane, 1, fft_kind<T>(), plane) ==
+              CUFFT_SUCCESS;
+    xy_first_[0] = 0, xy_count_[0] = (int)((ms[2] - 1) / 2 + 1);        // kz = 0 .. kmax
+    xy_first_[1] = nf[2] - ms[2] / 2, xy_count_[1] = (int)(ms[2] / 2);  // kz = -ms/2 .. -1
+    int nxy[2] = {(int)nf[1], (int)nf[0]};
+    int made = 0;
+    for (int r = 0; r < 2 && ok; ++r) {
+      if (!xy_count_[r]) continue;
+      ok = cufftPlanMany(&fftxy_[r], 2, nxy, nullptr, 1, plane, nullptr, 1, plane, fft_kind<T>(),
+                         xy_count_[r]) == CUFFT_SUCCESS;
+      if (ok) ++made;
+    }
+    if (!ok) {  // fall back to the plain 3D plan
+      if (fftz_) cufftDestroy(fftz_);
+      for (int r = 0, k = 0; r < 2 && k < made; ++r)
+        if (xy_count_[r]) cufftDestroy(fftxy_[r]), ++k;
+      xy_count_[0] = xy_count_[1] = 0;
+    } else {
+      pruned_ = true;
+      bool sok = cufftSetStream(fftz_, st) == CUFFT_SUCCESS;
+      for (int r = 0; r < 2; ++r)
+        if (xy_count_[r]) sok = sok && cufftSetStream(fftxy_[r], st) == CUFFT_SUCCESS;
+      if (!sok) throw Failure{ERR_CUDA_FAILURE};
+      return;
+    }
+  }
   if (cufftPlanMany(&fft_, dim, n, nullptr, 1, (int)total, nullptr, 1, (int)total, fft_kind<T>(),
                     batch) != CUFFT_SUCCESS)
     throw Failure{ERR_CUDA_FAILURE};
@@ -570,7 +629,7 @@ void Engine<T>::spread_path(C *c, C *fk, int fsign, const ExecHooks *hooks) {
       if (hooks && hooks->after_modes) hooks->after_modes(b0, nb);
       continue;
     }
-    fft_exec(fft_, fw_.p, fsign);
+    fft_grid(fw_.p, nb, fsign, true);
     mark(2);
     launch_grid_to_modes<T>(dim, nb, fw_.p, fk + (int64_t)b0 * Nm, mg, st);
     ++launches;
@@ -606,7 +665,7 @@ void Engine<T>::interp_path(C *c, C *fk, int fsign, const ExecHooks *hooks) {
       launch_modes_to_grid<T>(dim, nb, fk + (int64_t)b0 * Nm, fw_.p, mg, st);
       ++launches;
       mark(1);
-      fft_exec(fft_, fw_.p, fsign);
+      fft_grid(fw_.p, nb, fsign, false);
       mark(2);
     }
     const int ngrp = (int)geom.nchunks;

@@ -38,6 +38,7 @@ struct EngineOpts {
   int debug            = 0;
   int allow_eps_too_small = 1;
   int sort_radix       = 0;     // 1: stable radix sort (reference permutation on the device)
+  int prune            = 1;     // 3D: skip the x,y transforms of the z-planes outside the mode band
   int sweep            = 1;     // 3D float: tube-sweep kernels (0 = generic kernels)
   int stage            = -1;    // two-level strength permutation (stage.cuh): -1 auto, 0 off, 1 on
   int check_sigma      = 0;     // host (finufft_*) entry points apply the CPU feasibility rule
@@ -132,6 +133,15 @@ template<class T> class Engine {
   DevBuf<C> fw_;
   cufftHandle fft_ = 0;
   bool have_fft_   = false;
+  // pruned 3D FFT: only ms3 of the nf3 z-planes carry wanted (type 1) or non-zero (type 2) data
+  // across the x,y transforms, so the 3D FFT is run as one batched 1D FFT along z plus batched
+  // 2D FFTs of those planes only (two contiguous ranges: kz >= 0 and kz < 0)
+  cufftHandle fftz_ = 0, fftxy_[2] = {0, 0};
+  int64_t xy_first_[2] = {0, 0};
+  int xy_count_[2]     = {0, 0};
+  bool pruned_         = false;
+  void fft_grid(C *grid, int nb, int fsign, bool spreading);
+  void destroy_fft();
   // point state
   DevBuf<T> xs_, ys_, zs_;
   DevBuf<uint32_t> sidx_, binstart_, sub_bin_, sub_off_;
