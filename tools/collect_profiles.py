@@ -76,10 +76,10 @@ if os.path.exists(lc):
     setp = {k: sum(v) / len(v) for k, v in ms.items() if k.startswith(("k_bin_count", "k_bin_place", "k_refine"))}
     txt = f"""# {tag}: ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-cpu`
 # (profiles/{tag}_launches_c3_t1.csv; per-launch times are cold-cache/serialised: the SHARE of the step counts)
-# one device-resident execute of C3 type 1 = memset(fw) + k_sweep3<7,1> + 3 cuFFT kernels + k_grid_to_modes
+# one device-resident execute of C3 type 1 = memset(fw) + k_sweep3<7,1> + cuFFT kernels (pruned 3D) + k_grid_to_modes
 kernel                     per-execute ms   share of execute kernels
 k_sweep3<7,1> (spread)     {sp:.3f}            {100 * sp / tot:.1f} %
-cuFFT (3 kernels)          {fft:.3f}            {100 * fft / tot:.1f} %
+cuFFT (all kernels)        {fft:.3f}            {100 * fft / tot:.1f} %
 k_grid_to_modes<float,3>   {dc:.3f}            {100 * dc / tot:.1f} %
 # bench.py stages_ms (CUDA events, same run family): spreadinterp {st['spreadinterp']:.3f} (incl. 0.17 ms memset), fft {st['fft']:.3f}, deconv {st['deconv']:.3f}
 # the e2e leg (finufft_execute, host pointers) spreads in 4 point groups: {len(grp)} k_sweep3 launches of {min(grp or [0]):.2f}..{max(grp or [0]):.2f} ms
