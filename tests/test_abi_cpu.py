@@ -111,3 +111,34 @@ def test_no_cpu_fallback(lib):
     assert not p.value
     hp = C.c_void_p()
     assert lib.finufft_makeplan(1, 3, nm, 1, 1, C.c_double(1e-6), C.byref(hp), None) == 15
+
+
+def test_c_caller_compiles_links_and_gets_the_no_device_code(tmp_path):
+    """A plain C99 program written against the reference's guru sequence (examples/guru3d1f.c)
+    compiles with the headers in include/, links against the shared library, and -- on a machine
+    without a CUDA device -- gets error 15 back from makeplan instead of any CPU fallback."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    import finufft_b200
+    finufft_b200.load()
+    libdir = os.path.join(ROOT, "finufft_b200")
+    exe = str(tmp_path / "guru3d1f")
+    subprocess.check_call(["gcc", "-std=c99", "-D_GNU_SOURCE", "-O1", "-Wall", "-Werror", "-I",
+                           os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "guru3d1f.c"), "-L", libdir,
+                           "-lfinufft_b200", "-lm", f"-Wl,-rpath,{libdir}", "-o", exe])
+    # headers are valid C++ too
+    cpp = tmp_path / "hdr.cpp"
+    cpp.write_text('#include "b200_finufft.h"\n#include "b200_cufinufft.h"\n'
+                   '#include "b200_introspect.h"\nint main() { return 0; }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                           str(cpp)])
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    rc = subprocess.call([exe])
+    assert rc == (0 if has_gpu else 15)
