@@ -75,9 +75,12 @@ template<class T> struct HostPlan : DevicePlan<T> {
 // Point groups of a host-pointer plan (engine.hpp set_point_groups): with one transform vector
 // of at least 64 MB, 4 groups let the spread of group k overlap the upload of group k+1 (and
 // the download of group k overlap the interpolation of k+1).  B200_NUFFT_HOST_GROUPS overrides.
-template<class T> int host_point_groups(int64_t M, int ntr, int type) {
+template<class T> int host_point_groups(int64_t M, int ntr, int type, int64_t grid_cells) {
   if (const char *env = getenv("B200_NUFFT_HOST_GROUPS")) return std::max(1, atoi(env));
   if (type == 3 || ntr > 1) return 1;  // many vectors pipeline vector by vector instead
+  // every group sweeps the whole grid, so splitting pays only for dense point sets (measured at
+  // 0.75 and 6 points per fine-grid cell); sparse ones keep one group
+  if (2 * M < grid_cells) return 1;
   return (uint64_t)M * sizeof(typename CxOf<T>::type) >= (64ull << 20) ? 4 : 1;
 }
 
@@ -254,7 +257,7 @@ int host_setpts(void *plan, int64_t M, const T *x, const T *y, const T *z, int64
     }
     p->M = M;
     p->N = N;
-    p->eng.set_point_groups(host_point_groups<T>(M, p->eng.ntr, p->eng.type));
+    p->eng.set_point_groups(host_point_groups<T>(M, p->eng.ntr, p->eng.type, p->eng.grid_cells()));
     p->eng.setpts(M, p->x.p, p->y.p, p->z.p, N, p->s.p, p->t.p, p->u.p);
   });
 }
