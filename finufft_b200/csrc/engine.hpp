@@ -152,7 +152,7 @@ template<class T> class Engine {
   bool swept_      = false;
   bool swept2_     = false;  // 2D sweep kernels (sweep2d.cuh) in use
   // two-level permutation of the strengths (stage.cuh)
-  DevBuf<uint32_t> perm1_, perm2_;
+  DevBuf<uint32_t> perm1_, perm2_, pinv_;
   DevBuf<C> mid_;
   bool staged_ = false;
   void build_staging();

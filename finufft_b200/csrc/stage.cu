@@ -40,7 +40,7 @@ k_stage_count(const uint32_t *__restrict__ sidx, uint32_t M, int shift, uint32_t
 __global__ void __launch_bounds__(256)
 k_stage_place(const uint32_t *__restrict__ sidx, uint32_t M, int shift, uint32_t nunits,
               const uint32_t *__restrict__ offsets, uint32_t *__restrict__ perm1,
-              uint32_t *__restrict__ perm2) {
+              uint32_t *__restrict__ perm2, uint32_t *__restrict__ pinv) {
   const int lane           = threadIdx.x & 31;
   const uint32_t lt_mask   = (1u << lane) - 1u;
   const uint32_t nwarps    = gridDim.x * (blockDim.x >> 5);
@@ -57,6 +57,7 @@ k_stage_place(const uint32_t *__restrict__ sidx, uint32_t M, int shift, uint32_t
         const uint32_t m = base + __popc(peers & lt_mask);
         perm1[q] = m;
         perm2[m] = j;
+        pinv[j]  = m;
       }
       // lane w advances its cursor by the size of window w's group
       uint32_t add = 0;
@@ -80,12 +81,13 @@ static inline int stage_grid(uint32_t nunits) {
 
 void build_stage_perms(const uint32_t *sidx, uint32_t M, int shift, uint32_t *counts,
                        uint32_t *offsets, uint32_t *scan_tmp, uint32_t *perm1, uint32_t *perm2,
-                       cudaStream_t st) {
+                       uint32_t *pinv, cudaStream_t st) {
   if (M == 0) return;
   const uint32_t nunits = (M + kStageUnit - 1) / kStageUnit;
   k_stage_count<<<stage_grid(nunits), 256, 0, st>>>(sidx, M, shift, nunits, counts);
   exclusive_scan_u32(counts, offsets, (uint32_t)kStageMaxWindows * nunits, scan_tmp, st);
-  k_stage_place<<<stage_grid(nunits), 256, 0, st>>>(sidx, M, shift, nunits, offsets, perm1, perm2);
+  k_stage_place<<<stage_grid(nunits), 256, 0, st>>>(sidx, M, shift, nunits, offsets, perm1, perm2,
+                                                    pinv);
 }
 
 template<class C>
@@ -96,13 +98,16 @@ k_stage_in(const C *__restrict__ c, const uint32_t *__restrict__ perm2, C *__res
   for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += stride)
     mid[m] = __ldg(c + __ldcs(perm2 + m));
 }
+// user order, coalesced writes; the reads stay inside the window of mid that belongs to the
+// window of j being written (a scatter c[perm2[m]] = mid[m] does not merge in the L2: measured
+// 3.1 ms and 2.9 GB of DRAM writes at C2, against 0.7 ms for this gather)
 template<class C>
 __global__ void __launch_bounds__(256)
-k_stage_out(const C *__restrict__ mid, const uint32_t *__restrict__ perm2, C *__restrict__ c,
+k_stage_out(const C *__restrict__ mid, const uint32_t *__restrict__ pinv, C *__restrict__ c,
             uint32_t M) {
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += stride)
-    c[__ldcs(perm2 + m)] = __ldcs(mid + m);
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += stride)
+    c[j] = __ldg(mid + __ldcs(pinv + j));
 }
 static inline int stream_grid(uint32_t n) {
   const uint32_t want = (n + 255) / 256;
@@ -113,8 +118,8 @@ void launch_stage_in(const C *c, const uint32_t *perm2, C *mid, uint32_t M, cuda
   if (M) k_stage_in<C><<<stream_grid(M), 256, 0, st>>>(c, perm2, mid, M);
 }
 template<class C>
-void launch_stage_out(const C *mid, const uint32_t *perm2, C *c, uint32_t M, cudaStream_t st) {
-  if (M) k_stage_out<C><<<stream_grid(M), 256, 0, st>>>(mid, perm2, c, M);
+void launch_stage_out(const C *mid, const uint32_t *pinv, C *c, uint32_t M, cudaStream_t st) {
+  if (M) k_stage_out<C><<<stream_grid(M), 256, 0, st>>>(mid, pinv, c, M);
 }
 template void launch_stage_in<float2>(const float2 *, const uint32_t *, float2 *, uint32_t,
                                       cudaStream_t);

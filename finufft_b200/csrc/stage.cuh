@@ -15,8 +15,10 @@
 //              line of c leaves HBM once; the spread kernel then reads mid[perm1[q]], K
 //              interleaved sequential streams that live in L1/L2;
 //   * type 2:  the interp kernel writes mid[perm1[q]] (K sequential write streams, merged in
-//              the L2), stage_out  c[perm2[m]] = mid[m]  scatters inside an L2-resident window.
-// perm1/perm2 are built once per setpts by a stable K-way partition of the sorted positions.
+//              the L2), stage_out  c[j] = mid[pinv[j]]  gathers inside an L2-resident window of
+//              mid and writes c coalesced (pinv = inverse of perm2; the scatter form
+//              c[perm2[m]] = mid[m] does not merge in the L2 and was measured slower).
+// perm1/perm2/pinv are built once per setpts by a stable K-way partition of the sorted positions.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -31,14 +33,14 @@ constexpr uint32_t kStageUnit  = 1024;  // sorted positions one warp partitions
 int stage_shift(uint64_t M, int elem_bytes);
 
 // scratch: counts (K * nunits + 1 words, nunits = ceil(M / kStageUnit)), scan_tmp as for
-// exclusive_scan_u32.  Writes perm1[M], perm2[M].
+// exclusive_scan_u32.  Writes perm1[M], perm2[M], pinv[M].
 void build_stage_perms(const uint32_t *sidx, uint32_t M, int shift, uint32_t *counts,
                        uint32_t *offsets, uint32_t *scan_tmp, uint32_t *perm1, uint32_t *perm2,
-                       cudaStream_t st);
+                       uint32_t *pinv, cudaStream_t st);
 
 template<class C>
 void launch_stage_in(const C *c, const uint32_t *perm2, C *mid, uint32_t M, cudaStream_t st);
 template<class C>
-void launch_stage_out(const C *mid, const uint32_t *perm2, C *c, uint32_t M, cudaStream_t st);
+void launch_stage_out(const C *mid, const uint32_t *pinv, C *c, uint32_t M, cudaStream_t st);
 
 }  // namespace b200
