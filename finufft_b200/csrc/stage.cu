@@ -12,27 +12,28 @@ int stage_shift(uint64_t M, int elem_bytes) {
   return shift;
 }
 
-// counts[w * nunits + u] = sorted positions of unit u whose user index lies in window w
+// counts[w * nunits + u] = sorted positions of unit u whose user index lies in window w.
+// One warp per unit; per-warp counters in shared memory, one atomic per distinct window and
+// round (warp-aggregated with match_any).
 __global__ void __launch_bounds__(256)
 k_stage_count(const uint32_t *__restrict__ sidx, uint32_t M, int shift, uint32_t nunits,
               uint32_t *__restrict__ counts) {
-  const int lane = threadIdx.x & 31;
+  __shared__ uint32_t scnt[8][kStageMaxWindows];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < nunits; u += nwarps) {
+  for (uint32_t u = blockIdx.x * (blockDim.x >> 5) + warp; u < nunits; u += nwarps) {
     const uint32_t q0 = u * kStageUnit, q1 = min(M, q0 + kStageUnit);
-    uint32_t mine = 0;  // lane w counts window w
+    scnt[warp][lane] = 0;
+    __syncwarp();
     for (uint32_t q = q0 + lane; q < q0 + kStageUnit; q += 32) {
-      const uint32_t w = q < q1 ? sidx[q] >> shift : 0xffffffffu;
-#pragma unroll 1
-      for (uint32_t left = __activemask(); left;) {  // one ballot per distinct window
-        const uint32_t lead = __ffs(left) - 1;
-        const uint32_t wl   = __shfl_sync(0xffffffffu, w, lead);
-        const uint32_t same = __ballot_sync(0xffffffffu, w == wl);
-        if (wl != 0xffffffffu && (uint32_t)lane == wl) mine += __popc(same);
-        left &= ~same;
-      }
+      const bool valid     = q < q1;
+      const uint32_t w     = valid ? __ldcs(sidx + q) >> shift : 0xffffffffu;
+      const uint32_t peers = __match_any_sync(0xffffffffu, w);
+      if (valid && lane == __ffs(peers) - 1) scnt[warp][w] += __popc(peers);
+      __syncwarp();
     }
-    if (lane < kStageMaxWindows) counts[(size_t)lane * nunits + u] = mine;
+    counts[(size_t)lane * nunits + u] = scnt[warp][lane];
+    __syncwarp();
   }
 }
 
@@ -41,35 +42,29 @@ __global__ void __launch_bounds__(256)
 k_stage_place(const uint32_t *__restrict__ sidx, uint32_t M, int shift, uint32_t nunits,
               const uint32_t *__restrict__ offsets, uint32_t *__restrict__ perm1,
               uint32_t *__restrict__ perm2, uint32_t *__restrict__ pinv) {
-  const int lane           = threadIdx.x & 31;
-  const uint32_t lt_mask   = (1u << lane) - 1u;
-  const uint32_t nwarps    = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < nunits; u += nwarps) {
+  __shared__ uint32_t srun[8][kStageMaxWindows];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t nwarps  = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t u = blockIdx.x * (blockDim.x >> 5) + warp; u < nunits; u += nwarps) {
     const uint32_t q0 = u * kStageUnit, q1 = min(M, q0 + kStageUnit);
-    uint32_t run = lane < kStageMaxWindows ? offsets[(size_t)lane * nunits + u] : 0u;
+    srun[warp][lane] = offsets[(size_t)lane * nunits + u];
+    __syncwarp();
     for (uint32_t q = q0 + lane; q < q0 + kStageUnit; q += 32) {
-      const bool valid = q < q1;
-      const uint32_t j = valid ? sidx[q] : 0u;
-      const uint32_t w = valid ? j >> shift : 0xffffffffu;
+      const bool valid     = q < q1;
+      const uint32_t j     = valid ? __ldcs(sidx + q) : 0u;
+      const uint32_t w     = valid ? j >> shift : 0xffffffffu;
       const uint32_t peers = __match_any_sync(0xffffffffu, w);
-      const uint32_t base  = __shfl_sync(0xffffffffu, run, valid ? w : 0);
+      uint32_t m           = 0;
+      if (valid) m = srun[warp][w] + __popc(peers & lt_mask);
+      __syncwarp();
       if (valid) {
-        const uint32_t m = base + __popc(peers & lt_mask);
         perm1[q] = m;
         perm2[m] = j;
         pinv[j]  = m;
+        if (lane == __ffs(peers) - 1) srun[warp][w] += __popc(peers);
       }
-      // lane w advances its cursor by the size of window w's group
-      uint32_t add = 0;
-#pragma unroll 1
-      for (uint32_t left = __ballot_sync(0xffffffffu, valid); left;) {
-        const uint32_t lead = __ffs(left) - 1;
-        const uint32_t wl   = __shfl_sync(0xffffffffu, w, lead);
-        const uint32_t grp  = __shfl_sync(0xffffffffu, peers, lead);
-        if ((uint32_t)lane == wl) add = __popc(grp);
-        left &= ~grp;
-      }
-      run += add;
+      __syncwarp();
     }
   }
 }
