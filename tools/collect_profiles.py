@@ -96,6 +96,7 @@ for name, (obj, sym) in objs.items():
     if not os.path.exists(o):
         continue
     out = subprocess.run(["cuobjdump", "-sass", o, "-fun", sym], capture_output=True, text=True).stdout
-    lines = [ln.strip().split("/* 0x")[0].rstrip() for ln in out.splitlines() if ln.strip().startswith("/*") and "*/" in ln[:12]]
+    lines = [ln.strip().split("/* 0x")[0].rstrip() for ln in out.splitlines()
+             if ln.strip().startswith("/*") and "*/" in ln.strip()[:12]]
     open(os.path.join(P, f"{tag}_sass_{name}.txt"), "w").write("\n".join(lines) + "\n")
 print("profiles/ updated for", tag)
