@@ -42,33 +42,12 @@ template<int NS> struct SweepCfg {
   static_assert(HL <= XB && NS <= 7 && RZ <= 3, "layout");
 };
 
-// Horner table padded to 8 columns so that two neighbouring panels form one aligned pair:
-// c[k*8 + j], k = 0 highest degree, columns j >= NS are zero.
-template<int NS> struct alignas(16) PairTable {
-  float c[TableRows<NS>::value * 8];
-};
-// NS window values by packed Horner (two panels per FFMA2); same roundings as eval_window.
-template<int NS>
-__device__ __forceinline__ void eval_window2(const PairTable<NS> &tab, float x1, float (&out)[8]) {
-  const float z = fma_rn(2.0f, x1, (float)(NS - 1));
-  float2 r[4];
-#pragma unroll
-  for (int p = 0; p < (NS + 1) / 2; ++p) {
-    r[p] = *reinterpret_cast<const float2 *>(&tab.c[2 * p]);
-#pragma unroll
-    for (int k = 1; k < TableRows<NS>::value; ++k)
-      r[p] = ffma2_s(z, r[p], *reinterpret_cast<const float2 *>(&tab.c[k * 8 + 2 * p]));
-    out[2 * p]     = r[p].x;
-    out[2 * p + 1] = r[p].y;
-  }
-}
-
 template<int NS> struct SweepArgs {
   const float *xs, *ys, *zs;   // coordinates, refined bin order
   const uint32_t *sidx;        // position -> user index
   const SweepItem *items;
   GridGeom<float> g;
-  PairTable<NS> tab;
+  typename SweepTab<float, NS>::type tab;
   const float2 *c_in;
   float2 *c_out;
   float2 *fw;
@@ -90,7 +69,7 @@ __device__ __forceinline__ void make_record(const SweepArgs<NS> &a, const RawPoi
   float x1;
   float kv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   stencil_start<float, NS>(fold_rescale<float>(pt.x, a.g.nf_t[0]), i0, x1);
-  eval_window2<NS>(a.tab, x1, kv);
+  eval_window_t(a.tab, x1, kv);
   const int gpos = (i0 + CF::XB) >> 1;  // window start 2*gpos - XB <= i0 <= that + 1
   // rotate: the weight of stencil cell t belongs to the window row x = i0 + t (mod 8)
 #pragma unroll
@@ -98,13 +77,13 @@ __device__ __forceinline__ void make_record(const SweepArgs<NS> &a, const RawPoi
 #pragma unroll
   for (int s = 0; s < 8; ++s) kv[s] = 0.f;
   stencil_start<float, NS>(fold_rescale<float>(pt.y, a.g.nf_t[1]), i0, x1);
-  eval_window2<NS>(a.tab, x1, kv);
+  eval_window_t(a.tab, x1, kv);
   const int jb = min(max(i0 - (kBinY * i2 - CF::HL), 0), kBinY);
   kv[7]        = __int_as_float((gpos << 4) | jb);
   *reinterpret_cast<float4 *>(rec)     = make_float4(kv[0], kv[1], kv[2], kv[3]);
   *reinterpret_cast<float4 *>(rec + 4) = make_float4(kv[4], kv[5], kv[6], kv[7]);
   stencil_start<float, NS>(fold_rescale<float>(pt.z, a.g.nf_t[2]), i0, x1);
-  eval_window2<NS>(a.tab, x1, kv);
+  eval_window_t(a.tab, x1, kv);
   // z stencil start relative to the tile's first z row, in [0, kBinZ]
   const int k0 = min(max(i0 - (kBinZ * i3 - CF::HL), 0), kBinZ);
   // tile row z = k0 + t lives in word 16 + 4*(z & 3) + (z >> 2)
@@ -420,12 +399,7 @@ static cudaError_t launch_ns(const SweepPoints &pts, const GridGeom<float> &g, i
   SweepArgs<NS> a;
   a.xs = pts.xs, a.ys = pts.ys, a.zs = pts.zs, a.sidx = pts.sidx, a.items = pts.items;
   a.g = g;
-  constexpr int rows = TableRows<NS>::value;
-  for (int k = 0; k < rows; ++k)
-    for (int j = 0; j < 8; ++j) {
-      const int src      = k - (rows - nc);
-      a.tab.c[k * 8 + j] = (src >= 0 && j < NS) ? coef[src * NS + j] : 0.f;
-    }
+  fill_table(a.tab, nc, coef);
   a.c_in  = c_in;
   a.c_out = c_out;
   a.fw    = fw;

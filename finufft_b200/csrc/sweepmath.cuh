@@ -3,8 +3,9 @@
 // compile-time loops, and the packed Horner evaluation of the window polynomials.
 //
 // Spec of the window evaluation: include/finufft/spreadinterp.hpp:85-92 (reference CPU, scalar
-// Horner, highest degree first, fused multiply-add per step); the packed form evaluates two
-// panels per instruction with exactly the same roundings.
+// Horner, highest degree first, fused multiply-add per step).  PairTab evaluates two panels per
+// instruction with exactly the same roundings; EOTab (the default for float) uses the even/odd
+// symmetry of the window and agrees to ~1 ulp of the window peak.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -61,9 +62,42 @@ template<int NS> struct alignas(16) PairTab {
   static constexpr int ROWS = TableRows<NS>::value;
   float c[ROWS * COLS];
 };
-// the table a kernel carries: packed pairs for float, the plain layout for double
+// Even/odd form of the same polynomials (float).  The window is even, so panel NS-1-j is panel j
+// mirrored: p_{NS-1-j}(z) = p_j(-z), i.e. p_j = E(z^2) + z O(z^2) and its mirror E - z O: one
+// packed Horner in z^2 on the pair (E, O) gives two window values (the reference CPU library
+// evaluates this way when its SIMD width is below NS, include/finufft/simd.hpp:373-422).
+// c[i][p] = (coefficient of z^(2i), coefficient of z^(2i+1)) of panel p, p < (NS+1)/2.  The fitted
+// table is symmetric to rounding only, so results differ from the plain Horner form by ~1 ulp of
+// the window peak (checked: <= 2.4e-7 absolute in float).
+template<int NS> struct alignas(16) EOTab {
+  static constexpr int ROWS = TableRows<NS>::value;
+  static constexpr int NE   = (ROWS + 1) / 2;  // terms of E (O is padded to the same count)
+  static constexpr int NP   = (NS + 1) / 2;    // panel pairs (the middle panel pairs with itself)
+  float2 c[NE * NP];
+};
+#ifndef B200_EVENODD
+#define B200_EVENODD 1
+#endif
+// the table a kernel carries: packed for float, the plain layout for double
 template<class T, int NS> struct SweepTab { using type = WindowTable<T, NS>; };
+#if B200_EVENODD
+template<int NS> struct SweepTab<float, NS> { using type = EOTab<NS>; };
+#else
 template<int NS> struct SweepTab<float, NS> { using type = PairTab<NS>; };
+#endif
+
+template<int NS> __host__ inline void fill_table(EOTab<NS> &tab, int nc, const float *coef) {
+  constexpr int ROWS = EOTab<NS>::ROWS;
+  // a(d, j) = coefficient of z^d of panel j; table rows are highest degree first, padded on top
+  auto a = [&](int d, int j) -> float {
+    if (d > ROWS - 1) return 0.f;
+    const int src = (ROWS - 1 - d) - (ROWS - nc);
+    return src >= 0 ? coef[src * NS + j] : 0.f;
+  };
+  for (int i = 0; i < EOTab<NS>::NE; ++i)
+    for (int p = 0; p < EOTab<NS>::NP; ++p)
+      tab.c[i * EOTab<NS>::NP + p] = float2{a(2 * i, p), a(2 * i + 1, p)};
+}
 
 template<int NS>
 __host__ inline void fill_table(PairTab<NS> &tab, int nc, const float *coef) {
@@ -96,6 +130,20 @@ __device__ __forceinline__ void eval_window_t(const PairTab<NS> &tab, float x1, 
       r = ffma2_s(z, r, *reinterpret_cast<const float2 *>(&tab.c[k * COLS + 2 * p]));
     out[2 * p]     = r.x;
     out[2 * p + 1] = r.y;
+  }
+}
+template<int NS>
+__device__ __forceinline__ void eval_window_t(const EOTab<NS> &tab, float x1, float *out) {
+  constexpr int NE = EOTab<NS>::NE, NP = EOTab<NS>::NP;
+  const float z  = fma_rn(2.0f, x1, (float)(NS - 1));
+  const float z2 = mul_rn(z, z);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    float2 r = tab.c[(NE - 1) * NP + p];
+#pragma unroll
+    for (int i = NE - 2; i >= 0; --i) r = ffma2_s(z2, r, tab.c[i * NP + p]);
+    out[p] = fma_rn(z, r.y, r.x);
+    if (NS - 1 - p != p) out[NS - 1 - p] = fma_rn(-z, r.y, r.x);
   }
 }
 template<class T, int NS>
