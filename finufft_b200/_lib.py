@@ -80,7 +80,8 @@ SIMPLE_GPU = [f"cufinufft{p}{d}d{t}{m}" for p in ("", "f") for d in (1, 2, 3)
               for t in (1, 2, 3) for m in ("", "many")]
 SIMPLE_HOST = [f"finufft{p}{d}d{t}{m}" for p in ("", "f") for d in (1, 2, 3)
                for t in (1, 2, 3) for m in ("", "many")]
-INTROSPECT = ["b200_get_plan_info", "b200_get_sort_permutation", "b200_get_window_table",
+INTROSPECT = ["b200_get_plan_info", "b200_get_sort_permutation", "b200_get_raw_sort_order",
+              "b200_get_sort_path", "b200_get_window_table",
               "b200_get_phihat", "b200_enable_profiling", "b200_get_stage_ms",
               "b200_get_launch_count", "b200_host_kernel", "b200_host_fine_grid",
               "b200_host_fseries", "b200_version"]
@@ -135,6 +136,10 @@ def load():
     lib.b200_get_plan_info.restype = ci
     lib.b200_get_sort_permutation.argtypes = [vp, vp]
     lib.b200_get_sort_permutation.restype = ci
+    lib.b200_get_raw_sort_order.argtypes = [vp, vp]
+    lib.b200_get_raw_sort_order.restype = ci
+    lib.b200_get_sort_path.argtypes = [vp, C.POINTER(ci)]
+    lib.b200_get_sort_path.restype = ci
     lib.b200_get_window_table.argtypes = [vp, vp]
     lib.b200_get_window_table.restype = ci
     lib.b200_get_phihat.argtypes = [vp, ci, vp]

@@ -296,6 +296,16 @@ template<class T> int host_execute(void *plan, void *c, void *fk, bool adjoint) 
     }
     if (!p->s_in) check_cuda(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
     if (!p->s_out) check_cuda(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    // Whatever happens below (a CUDA error, an engine failure), no copy that reads or writes
+    // the caller's host buffers may still be in flight when this call returns.
+    struct Drain {
+      cudaStream_t a, b, c;
+      ~Drain() {
+        cudaStreamSynchronize(a);
+        cudaStreamSynchronize(b);
+        cudaStreamSynchronize(c);
+      }
+    } drain{st, p->s_in, p->s_out};
     const int ngrp      = p->eng.point_groups();
     const int64_t glen  = ngrp > 1 ? p->eng.group_len() : M;
     const int batch     = p->eng.batch;
@@ -686,6 +696,27 @@ int b200_get_sort_permutation(void *plan, uint32_t *host_out) {
       DeviceGuard g(as_plan<double>(plan)->eng.opts.device);
       as_plan<double>(plan)->eng.copy_sort_to_host(host_out);
     }
+  });
+}
+int b200_get_raw_sort_order(void *plan, uint32_t *host_out) {
+  return guarded([&] {
+    auto *b = static_cast<PlanBase *>(plan);
+    if (!b || b->magic != kMagic) throw Failure{ERR_PLAN_NOTVALID};
+    if (b->is_float) {
+      DeviceGuard g(as_plan<float>(plan)->eng.opts.device);
+      as_plan<float>(plan)->eng.copy_sort_to_host(host_out, true);
+    } else {
+      DeviceGuard g(as_plan<double>(plan)->eng.opts.device);
+      as_plan<double>(plan)->eng.copy_sort_to_host(host_out, true);
+    }
+  });
+}
+int b200_get_sort_path(void *plan, int *path) {
+  return guarded([&] {
+    auto *b = static_cast<PlanBase *>(plan);
+    if (!b || b->magic != kMagic || !path) throw Failure{ERR_PLAN_NOTVALID};
+    *path = b->is_float ? as_plan<float>(plan)->eng.sort_path()
+                        : as_plan<double>(plan)->eng.sort_path();
   });
 }
 int b200_get_window_table(void *plan, void *host_out) {

@@ -7,7 +7,11 @@
 #include <cstdlib>
 #include <limits>
 
+#include <mutex>
+
+#include "partition.cuh"
 #include "planmath.hpp"
+#include "scratch.hpp"
 #include "spreadinterp.cuh"
 #include "sweep3d.cuh"
 
@@ -21,6 +25,49 @@ static void cuda_check(cudaError_t e, const char *what) {
   throw Failure{e == cudaErrorMemoryAllocation ? ERR_ALLOC : ERR_CUDA_FAILURE};
 }
 #define CU(x) cuda_check((x), #x)
+
+// ------------------------------------------------------------------ scratch pool (scratch.hpp)
+namespace {
+constexpr int kMaxDevices = 64;
+std::mutex pool_mutex;
+cudaMemPool_t pools[kMaxDevices] = {};
+bool pool_tried[kMaxDevices]     = {};
+int pool_users[kMaxDevices]      = {};
+}  // namespace
+cudaMemPool_t scratch_pool(int device) {
+  if (device < 0 || device >= kMaxDevices) return nullptr;
+  std::lock_guard<std::mutex> lock(pool_mutex);
+  if (!pool_tried[device]) {
+    pool_tried[device] = true;
+    cudaMemPoolProps props{};
+    props.allocType     = cudaMemAllocationTypePinned;
+    props.handleTypes   = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id   = device;
+    cudaMemPool_t pool  = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+      uint64_t keep = ~0ull;  // freed blocks stay cached while plans live; trimmed at release
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      pools[device] = pool;
+    }
+    cudaGetLastError();
+  }
+  return pools[device];
+}
+void scratch_pool_retain(int device) {
+  if (device < 0 || device >= kMaxDevices) return;
+  std::lock_guard<std::mutex> lock(pool_mutex);
+  ++pool_users[device];
+}
+void scratch_pool_release(int device) {
+  if (device < 0 || device >= kMaxDevices) return;
+  std::lock_guard<std::mutex> lock(pool_mutex);
+  if (--pool_users[device] <= 0) {
+    pool_users[device] = 0;
+    if (pools[device]) cudaMemPoolTrimTo(pools[device], 0);  // back to the driver
+    cudaGetLastError();
+  }
+}
 
 template<class T> void DevBuf<T>::alloc(size_t count) {
   if (count <= n && p) return;
@@ -74,14 +121,8 @@ Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr
   if (dim < 1 || dim > 3) throw Failure{ERR_DIM_NOTVALID};
   if (ntr < 1) throw Failure{ERR_NTRANS_NOTVALID};
   DeviceGuard guard(opts.device);
-  {  // setpts scratch comes from the stream-ordered pool: keep freed blocks cached across calls
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, opts.device) == cudaSuccess) {
-      uint64_t keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    cudaGetLastError();
-  }
+  scratch_pool_retain(opts.device);  // setpts scratch: the library's own pool (scratch.hpp)
+  pool_held_ = true;
   tol   = tol_;
   sigma = opts.upsampfac == 0.0 ? 2.0 : opts.upsampfac;
   batch = opts.maxbatch > 0 ? std::min(opts.maxbatch, ntr) : std::min(ntr, 8);
@@ -90,6 +131,7 @@ Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr
   if (const char *env = getenv("B200_NUFFT_SORT")) opts.sort_radix = atoi(env) == 2;
   if (const char *env = getenv("B200_NUFFT_STAGE")) opts.stage = atoi(env);
   if (const char *env = getenv("B200_NUFFT_PRUNE")) opts.prune = atoi(env);
+  if (const char *env = getenv("B200_NUFFT_PART")) opts.partition = atoi(env);
   plan_kernel();
   if (type != 3) {
     for (int d = 0; d < dim; ++d) ms[d] = nmodes[d];
@@ -129,6 +171,11 @@ template<class T> void Engine<T>::fft_grid(C *grid, int nb, int fsign, bool spre
 }
 
 template<class T> Engine<T>::~Engine() {
+  if (pool_held_) {
+    // pending frees of this plan's stream must land before the pool can give memory back
+    cudaStreamSynchronize(opts.stream);
+    scratch_pool_release(opts.device);
+  }
   destroy_fft();
   for (auto &e : ev_)
     if (e) cudaEventDestroy(e);
@@ -268,20 +315,6 @@ template<class T> void Engine<T>::plan_grid() {
 }
 
 // ------------------------------------------------------------------ setpts
-// scratch that lives for one setpts call, from the stream-ordered pool (no device-wide syncs)
-template<class U> struct Scratch {
-  U *p            = nullptr;
-  cudaStream_t st = nullptr;
-  Scratch(size_t n, cudaStream_t s) : st(s) {
-    if (n) CU(cudaMallocAsync((void **)&p, n * sizeof(U), s));
-  }
-  ~Scratch() {
-    if (p) cudaFreeAsync(p, st);
-  }
-  Scratch(const Scratch &)            = delete;
-  Scratch &operator=(const Scratch &) = delete;
-};
-
 static uint32_t sweep2_item_points() {
   const char *e = getenv("B200_SWEEP2_ITEM");
   const long v  = e ? atol(e) : 0;
@@ -295,11 +328,11 @@ static uint32_t sweep3_item_points() {
 // refined order inside the bins for the sweep kernels; work units = 512-point chunks of bins
 static void refine_impl(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
                         uint32_t *sidx, const uint32_t *binstart, const GridGeom<float> &g,
-                        uint64_t M, uint32_t *scan_tmp, cudaStream_t st) {
+                        uint64_t M, uint32_t *scan_tmp, cudaStream_t st, int dev) {
   const uint32_t max_chunks =
       (uint32_t)(M / kRefineChunk + std::min<uint64_t>(g.nbins, M));
-  Scratch<uint32_t> nch(g.nbins, st), chstart((size_t)g.nbins + 1, st);
-  Scratch<uint32_t> chunk_bin(max_chunks, st), chunk_off(max_chunks, st);
+  Scratch<uint32_t> nch(g.nbins, st, dev), chstart((size_t)g.nbins + 1, st, dev);
+  Scratch<uint32_t> chunk_bin(max_chunks, st, dev), chunk_off(max_chunks, st, dev);
   launch_sub_count(binstart, g.nbins, kRefineChunk, nch.p, st);
   exclusive_scan_u32(nch.p, chstart.p, g.nbins, scan_tmp, st);
   launch_sub_fill(binstart, chstart.p, g.nbins, kRefineChunk, chunk_bin.p, chunk_off.p, st);
@@ -308,16 +341,16 @@ static void refine_impl(int ns, const Packed4<float> *packed, float *xs, float *
 }
 static void refine_impl(int, const Packed4<double> *, double *, double *, double *, uint32_t *,
                         const uint32_t *, const GridGeom<double> &, uint64_t, uint32_t *,
-                        cudaStream_t) {}
+                        cudaStream_t, int) {}
 // the same for the 2D sweep kernels (any precision)
 template<class T>
 static void refine2_impl(int ns, const Packed4<T> *packed, T *xs, T *ys, uint32_t *sidx,
                          const uint32_t *binstart, const GridGeom<T> &g, uint64_t M,
-                         uint32_t *scan_tmp, cudaStream_t st) {
+                         uint32_t *scan_tmp, cudaStream_t st, int dev) {
   const uint32_t max_chunks =
       (uint32_t)(M / kRefineChunk + std::min<uint64_t>(g.nbins, M));
-  Scratch<uint32_t> nch(g.nbins, st), chstart((size_t)g.nbins + 1, st);
-  Scratch<uint32_t> chunk_bin(max_chunks, st), chunk_off(max_chunks, st);
+  Scratch<uint32_t> nch(g.nbins, st, dev), chstart((size_t)g.nbins + 1, st, dev);
+  Scratch<uint32_t> chunk_bin(max_chunks, st, dev), chunk_off(max_chunks, st, dev);
   launch_sub_count(binstart, g.nbins, kRefineChunk, nch.p, st);
   exclusive_scan_u32(nch.p, chstart.p, g.nbins, scan_tmp, st);
   launch_sub_fill(binstart, chstart.p, g.nbins, kRefineChunk, chunk_bin.p, chunk_off.p, st);
@@ -327,6 +360,7 @@ static void refine2_impl(int ns, const Packed4<T> *packed, T *xs, T *ys, uint32_
 
 template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z) {
   cudaStream_t st = opts.stream;
+  const int dev   = opts.device;
   const uint32_t m = (uint32_t)M;
   // point groups (sort.cuh): group-major sort keys; needs the counting sort
   {
@@ -342,34 +376,48 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
   sidx_.alloc(M);
   binstart_.alloc((size_t)geom.nbins + 1);
   const size_t scan_n = std::max<size_t>(geom.nbins + 1, 256 * (size_t)kRadixMaxBlocks + 1);
-  Scratch<uint32_t> scan_tmp(scan_n / 4096 + 8, st);
+  Scratch<uint32_t> scan_tmp(scan_n / 4096 + 8, st, dev);
   // 3D float with a supported width: the sweep kernels want the order inside the bins refined
   swept_ = std::is_same<T, float>::value && dim == 3 && sweep3_supported(ns) && opts.sweep &&
            nf[0] % 2 == 0 && M > 0;
   swept2_ = dim == 2 && sweep2_supported<T>(ns) && opts.sweep && M > 0;
   radix_order_ = opts.sort_radix != 0 && geom.nchunks == 1;
 
-  if (!radix_order_) {
+  // default: multi-level partition with sequential streams (partition.cuh); point sets with
+  // very dense segments (clustered input) and small or sparse ones take the counting sort below
+  bool partitioned = false;
+  part_used_       = false;
+  if (!radix_order_ && opts.partition) {
+    const int cls = swept_ ? kClassSweep3 : (swept2_ ? kClassSweep2 : kClassNone);
+    const PartPlan pp = plan_partition((uint64_t)M, geom.nbins, cls, ns, sizeof(T) == 8,
+                                       opts.partition > 1);
+    if (pp.ok)
+      partitioned = partition_sort<T>(dim, x, y, z, m, geom, pp, binstart_.p, xs_.p, ys_.p, zs_.p,
+                                      sidx_.p, scan_tmp.p, dev, st);
+    part_used_ = partitioned;
+  }
+  if (partitioned) {
+  } else if (!radix_order_) {
     // counting sort: bin counts (warp-aggregated atomics) -> scan -> placement -> gather
-    Scratch<uint32_t> keys(M, st), ranks(M, st), cnt(geom.nbins, st);
-    Scratch<Packed4<T>> packed(M, st);
+    Scratch<uint32_t> keys(M, st, dev), ranks(M, st, dev), cnt(geom.nbins, st, dev);
+    Scratch<Packed4<T>> packed(M, st, dev);
     CU(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * geom.nbins, st));
     launch_bin_count<T>(dim, x, y, z, m, geom, keys.p, ranks.p, cnt.p, packed.p, st);
     exclusive_scan_u32(cnt.p, binstart_.p, geom.nbins, scan_tmp.p, st);
     launch_bin_place(keys.p, ranks.p, binstart_.p, m, sidx_.p, st);
     if (swept_)
       refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
-                  scan_tmp.p, st);
+                  scan_tmp.p, st, dev);
     else if (swept2_)
       refine2_impl<T>(ns, packed.p, xs_.p, ys_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
-                      scan_tmp.p, st);
+                      scan_tmp.p, st, dev);
     else
       launch_gather_packed<T>(dim, packed.p, sidx_.p, m, xs_.p, ys_.p, zs_.p, st);
     CU(cudaGetLastError());
   } else {
     // stable LSD radix sort of (bin key, index): yields the reference permutation directly
-    Scratch<uint32_t> keys_a(M, st), keys_b(M, st), vals_b(M, st);
-    Scratch<uint32_t> hist(256 * (size_t)kRadixMaxBlocks + 1, st);
+    Scratch<uint32_t> keys_a(M, st, dev), keys_b(M, st, dev), vals_b(M, st, dev);
+    Scratch<uint32_t> hist(256 * (size_t)kRadixMaxBlocks + 1, st, dev);
     launch_bin_keys<T>(dim, x, y, z, m, geom, keys_a.p, st);
     int nbits = 0;
     while ((1ull << nbits) < (uint64_t)geom.nbins) ++nbits;
@@ -380,16 +428,16 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
       CU(cudaMemcpyAsync(sidx_.p, vals_b.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToDevice, st));
     launch_bin_bounds(sorted_keys, m, geom.nbins, binstart_.p, st);
     if (swept_ || swept2_) {
-      Scratch<Packed4<T>> packed(M, st);
-      Scratch<uint32_t> keys(M, st), ranks(M, st), cnt(geom.nbins, st);  // packs the coordinates
+      Scratch<Packed4<T>> packed(M, st, dev);
+      Scratch<uint32_t> keys(M, st, dev), ranks(M, st, dev), cnt(geom.nbins, st, dev);  // packs the coordinates
       CU(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * geom.nbins, st));
       launch_bin_count<T>(dim, x, y, z, m, geom, keys.p, ranks.p, cnt.p, packed.p, st);
       if (swept_)
         refine_impl(ns, packed.p, xs_.p, ys_.p, zs_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
-                    scan_tmp.p, st);
+                    scan_tmp.p, st, dev);
       else
         refine2_impl<T>(ns, packed.p, xs_.p, ys_.p, sidx_.p, binstart_.p, geom, (uint64_t)M,
-                        scan_tmp.p, st);
+                        scan_tmp.p, st, dev);
     } else
       launch_gather_coords<T>(dim, x, y, z, sidx_.p, m, xs_.p, ys_.p, zs_.p, st);
     CU(cudaGetLastError());
@@ -399,7 +447,7 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
   build_staging();
 
   // subproblem list of the generic kernels: every bin in chunks of at most maxsub points
-  Scratch<uint32_t> nsubs(geom.nbins, st), substart((size_t)geom.nbins + 1, st);
+  Scratch<uint32_t> nsubs(geom.nbins, st, dev), substart((size_t)geom.nbins + 1, st, dev);
   launch_sub_count(binstart_.p, geom.nbins, (uint32_t)opts.maxsub, nsubs.p, st);
   exclusive_scan_u32(nsubs.p, substart.p, geom.nbins, scan_tmp.p, st);
   uint32_t total = 0;
@@ -425,6 +473,7 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
 // L2, where every random 8/16-byte access costs a 128-byte line of HBM traffic.
 template<class T> void Engine<T>::build_staging() {
   cudaStream_t st = opts.stream;
+  const int dev   = opts.device;
   const uint64_t bytes = (uint64_t)M * sizeof(C);
   staged_ = opts.stage > 0;  // opt-in: pays for repeated 2D type-2 executes only
   (void)bytes;
@@ -437,7 +486,7 @@ template<class T> void Engine<T>::build_staging() {
   }
   const uint32_t nunits = ((uint32_t)M + kStageUnit - 1) / kStageUnit;
   const size_t ncnt     = (size_t)kStageMaxWindows * nunits;
-  Scratch<uint32_t> counts(ncnt, st), offsets(ncnt + 1, st), tmp(ncnt / 4096 + 8, st);
+  Scratch<uint32_t> counts(ncnt, st, dev), offsets(ncnt + 1, st, dev), tmp(ncnt / 4096 + 8, st, dev);
   perm1_.alloc(M);
   perm2_.alloc(M);
   pinv_.alloc(M);
@@ -449,9 +498,10 @@ template<class T> void Engine<T>::build_staging() {
 
 template<class T> void Engine<T>::build_sweep_items(uint32_t *scan_tmp) {
   cudaStream_t st = opts.stream;
+  const int dev   = opts.device;
   const uint32_t nrows1 = (uint32_t)geom.nb[1] * (uint32_t)geom.nb[2];
   const uint32_t nrows  = nrows1 * geom.nchunks;  // rows are group-major like the bins
-  Scratch<uint32_t> nit(nrows, st), itstart((size_t)nrows + 1, st);
+  Scratch<uint32_t> nit(nrows, st, dev), itstart((size_t)nrows + 1, st, dev);
   const uint32_t maxpts = swept2_ ? sweep2_item_points() : sweep3_item_points();
   launch_row_item_count(binstart_.p, nrows, (uint32_t)geom.nb[0], maxpts, nit.p, st);
   exclusive_scan_u32(nit.p, itstart.p, nrows, scan_tmp, st);
@@ -700,18 +750,34 @@ void Engine<T>::execute(C *c, C *fk, bool adjoint, const ExecHooks *hooks) {
   else interp_path(c, fk, fsign, hooks);
 }
 
-template<class T> void Engine<T>::copy_sort_to_host(uint32_t *out) const {
+template<class T> void Engine<T>::copy_sort_to_host(uint32_t *out, bool raw) const {
   if (M == 0) return;
-  cudaStreamSynchronize(opts.stream);
-  cuda_check(cudaMemcpy(out, sidx_.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToHost), "copy sort");
-  if (swept_ || swept2_ || !radix_order_) {
-    // The counting sort leaves a bin's points in arrival order and the sweep kernels re-order them; the reference's stable counting sort
-    // leaves them in ascending index order (include/finufft/spread.hpp:559-581), which is
-    // restored here for inspection.
+  cudaStream_t st = opts.stream;
+  if (raw || radix_order_) {  // the device order as it stands
+    cudaStreamSynchronize(st);
+    cuda_check(cudaMemcpy(out, sidx_.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToHost), "copy sort");
+    return;
+  }
+  // The bins and their ranges are the reference's; inside a bin the device order is (window
+  // class, index) or arrival order.  The reference's stable counting sort leaves a bin in
+  // ascending index order (include/finufft/spread.hpp:559-581): restore that on the device, on
+  // a copy.
+  Scratch<uint32_t> perm(M, st, opts.device), nbig(1, st, opts.device);
+  cuda_check(cudaMemcpyAsync(perm.p, sidx_.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToDevice, st),
+             "copy sort");
+  cuda_check(cudaMemsetAsync(nbig.p, 0, sizeof(uint32_t), st), "copy sort");
+  launch_canon_bins(perm.p, binstart_.p, geom.nbins, nbig.p, st);
+  uint32_t big = 0;
+  cuda_check(cudaMemcpyAsync(&big, nbig.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "copy sort");
+  cuda_check(cudaMemcpyAsync(out, perm.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToHost, st),
+             "copy sort");
+  cuda_check(cudaStreamSynchronize(st), "copy sort");
+  if (big) {  // bins beyond the kernel's shared-memory capacity (clustered input): host
     std::vector<uint32_t> bs((size_t)geom.nbins + 1);
     cuda_check(cudaMemcpy(bs.data(), binstart_.p, sizeof(uint32_t) * bs.size(),
                           cudaMemcpyDeviceToHost), "copy binstart");
-    for (uint32_t b = 0; b < geom.nbins; ++b) std::sort(out + bs[b], out + bs[b + 1]);
+    for (uint32_t b = 0; b < geom.nbins; ++b)
+      if (bs[b + 1] - bs[b] > 1024) std::sort(out + bs[b], out + bs[b + 1]);
   }
 }
 template<class T> void Engine<T>::copy_phihat_to_host(int d, T *out) const {

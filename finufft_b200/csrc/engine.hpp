@@ -42,6 +42,7 @@ struct EngineOpts {
   int sweep            = 1;     // 3D float: tube-sweep kernels (0 = generic kernels)
   int stage            = -1;    // two-level strength permutation (stage.cuh): -1 auto, 0 off, 1 on
   int check_sigma      = 0;     // host (finufft_*) entry points apply the CPU feasibility rule
+  int partition        = 1;     // setpts: 1 partition sort where it pays, 2 always, 0 counting sort
 };
 
 // Callbacks of a pipelined execute (host-pointer plans, capi.cu): the engine announces when it
@@ -99,7 +100,10 @@ template<class T> class Engine {
   int batch = 1;
   int64_t grid_cells() const { return nf[0] * nf[1] * nf[2]; }
   int64_t mode_count() const { return ms[0] * ms[1] * ms[2]; }
-  void copy_sort_to_host(uint32_t *out) const;
+  // raw = false: the reference permutation (bins in order, ascending index inside a bin);
+  // raw = true: the order the kernels work in
+  void copy_sort_to_host(uint32_t *out, bool raw = false) const;
+  int sort_path() const { return radix_order_ ? 2 : (part_used_ ? 1 : 0); }
   void copy_phihat_to_host(int d, T *out) const;
   cudaStream_t stream() const { return opts.stream; }
   // stage timing (CUDA events on the plan's stream) and launch accounting for benches
@@ -157,6 +161,8 @@ template<class T> class Engine {
   bool staged_ = false;
   void build_staging();
   bool radix_order_ = false;  // sidx_ is the reference permutation as it stands
+  bool part_used_   = false;  // the last setpts took the partition sort (partition.cuh)
+  bool pool_held_   = false;
   // type 3
   DevBuf<T> xp_[3], sp_[3];
   DevBuf<C> prephase_, deconv_, cp_, ck_;

@@ -715,6 +715,42 @@ void launch_row_item_fill(const uint32_t *binstart, const uint32_t *itemstart, u
                                                        items);
 }
 
+// Reference order inside every bin (ascending user index, include/finufft/spread.hpp:559-581)
+// from any order: one warp per bin, indices ranked by comparison in shared memory.  Bins with
+// more than kCanonCap points are left as they are and counted in *nbig.
+constexpr int kCanonCap = 1024, kCanonWarps = 8;
+__global__ void __launch_bounds__(kCanonWarps * 32)
+k_canon_bins(uint32_t *__restrict__ perm, const uint32_t *__restrict__ binstart, uint32_t nbins,
+             uint32_t *__restrict__ nbig) {
+  __shared__ uint32_t s[kCanonWarps][kCanonCap];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t nwarps = gridDim.x * kCanonWarps;
+  for (uint32_t b = blockIdx.x * kCanonWarps + warp; b < nbins; b += nwarps) {
+    const uint32_t q0 = binstart[b], n = binstart[b + 1] - q0;
+    if (n < 2) continue;
+    if (n > (uint32_t)kCanonCap) {
+      if (lane == 0) atomicAdd(nbig, 1u);
+      continue;
+    }
+    for (uint32_t k = lane; k < n; k += 32) s[warp][k] = perm[q0 + k];
+    __syncwarp();
+    for (uint32_t k = lane; k < n; k += 32) {
+      const uint32_t mine = s[warp][k];
+      uint32_t r = 0;
+      for (uint32_t q = 0; q < n; ++q) r += s[warp][q] < mine ? 1u : 0u;
+      perm[q0 + r] = mine;
+    }
+    __syncwarp();
+  }
+}
+void launch_canon_bins(uint32_t *perm, const uint32_t *binstart, uint32_t nbins, uint32_t *nbig,
+                       cudaStream_t st) {
+  if (nbins == 0) return;
+  const uint32_t want = (nbins + kCanonWarps - 1) / kCanonWarps;
+  k_canon_bins<<<want < 148u * 8 ? want : 148u * 8, kCanonWarps * 32, 0, st>>>(perm, binstart, nbins,
+                                                                              nbig);
+}
+
 __global__ void k_iota(uint32_t *v, uint32_t n) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = i;

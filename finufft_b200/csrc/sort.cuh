@@ -62,6 +62,11 @@ void launch_sub_fill(const uint32_t *binstart, const uint32_t *substart, uint32_
 
 void launch_iota(uint32_t *v, uint32_t n, cudaStream_t st);
 
+// perm (a copy of the sort order) -> ascending user index inside every bin of at most 1024
+// points; *nbig (zero on entry) counts the larger bins, which are left untouched.
+void launch_canon_bins(uint32_t *perm, const uint32_t *binstart, uint32_t nbins, uint32_t *nbig,
+                       cudaStream_t st);
+
 // --- counting sort by bin (the default setpts path) ----------------------------------------
 // Bin counting with warp-aggregated atomics, prefix scan of the counts, placement of every
 // index in its bin.  The order inside a bin is the order the atomics happened to return; the

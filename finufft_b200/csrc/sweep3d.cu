@@ -51,8 +51,16 @@ template<int NS> struct SweepArgs {
   const float2 *c_in;
   float2 *c_out;
   float2 *fw;
-  int dbg;  // experiment switches (0 in production)
+#ifdef B200_EXPERIMENTS
+  int dbg;  // experiment switches, compiled in only with -DB200_EXPERIMENTS (never in the library)
+#endif
 };
+// experiment switches cost nothing and cannot change results unless compiled in
+#ifdef B200_EXPERIMENTS
+#define B200_DBG(a, bit) ((a).dbg & (bit))
+#else
+#define B200_DBG(a, bit) 0
+#endif
 
 // raw data of one point, as prefetched
 struct RawPoint {
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
           // skip all-zero pieces (sparse rows); one integer test instead of four float compares
           const uint32_t bits = __float_as_uint(v.x) | __float_as_uint(v.y) |
                                 __float_as_uint(v.z) | __float_as_uint(v.w);
-          if ((bits << 1) != 0u && !(a.dbg & 1))
+          if ((bits << 1) != 0u && !B200_DBG(a, 1))
             atomicAdd(reinterpret_cast<float4 *>(a.fw + lineoff[k] + gx), v);
         }
       }
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
   };
   auto load_c = [&](uint32_t q, const RawPoint &r) {
     float2 c = make_float2(0.f, 0.f);
-    if (SPREAD && q < item.qb && !(a.dbg & 4)) c = __ldg(a.c_in + r.j);
+    if (SPREAD && q < item.qb && !B200_DBG(a, 4)) c = __ldg(a.c_in + r.j);
     return c;
   };
   RawPoint r1 = load_raw(item.qa + lane);
@@ -346,7 +354,7 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
     };
     int p      = 0;
     LaneRec nx = load(0);
-    while (!(a.dbg & 2)) {
+    while (!B200_DBG(a, 2)) {
       const int key = __float_as_int(nx.k1.w);
       if (key < 0) break;
       advance_to(2 * (key >> 4) - CF::XB);
@@ -403,7 +411,9 @@ static cudaError_t launch_ns(const SweepPoints &pts, const GridGeom<float> &g, i
   a.c_in  = c_in;
   a.c_out = c_out;
   a.fw    = fw;
-  a.dbg   = getenv("B200_SWEEP_DBG") ? atoi(getenv("B200_SWEEP_DBG")) : 0;
+#ifdef B200_EXPERIMENTS
+  a.dbg = getenv("B200_SWEEP_DBG") ? atoi(getenv("B200_SWEEP_DBG")) : 0;
+#endif
   const size_t shbytes = CF::STAGE_BYTES + CF::REC_BYTES + (SPREAD ? 0 : CF::PART_BYTES);
   auto kern            = k_sweep3<NS, SPREAD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -62,6 +62,20 @@ class _PlanCommon:
                "get_sort")
         return out
 
+    def raw_sort_order(self):
+        """The order the kernels work in (device array as setpts left it)."""
+        M = self.info()["M"]
+        out = np.zeros(M, dtype=np.uint32)
+        _check(self._lib.b200_get_raw_sort_order(self._plan, out.ctypes.data_as(C.c_void_p)),
+               "get_raw_sort")
+        return out
+
+    def sort_path(self):
+        """0 counting sort, 1 partition sort, 2 stable radix sort (last setpts)."""
+        v = C.c_int()
+        _check(self._lib.b200_get_sort_path(self._plan, C.byref(v)), "get_sort_path")
+        return v.value
+
     def window_table(self):
         i = self.info()
         out = np.zeros((i["nc"], i["ns"]), dtype=self._real)

@@ -20,6 +20,11 @@ typedef struct b200_plan_info {
 int b200_get_plan_info(void *plan, b200_plan_info *out);
 /* sort permutation (sorted position -> user index), M entries, to HOST memory */
 int b200_get_sort_permutation(void *plan, uint32_t *host_out);
+/* the order the kernels work in, as setpts left it on the device: bins ascending, inside a bin
+ * (window class of the sweep kernels, user index) */
+int b200_get_raw_sort_order(void *plan, uint32_t *host_out);
+/* which sort the last setpts ran: 0 counting sort, 1 partition sort, 2 stable radix sort */
+int b200_get_sort_path(void *plan, int *path);
 /* polynomial table, nc*ns entries of the plan's real type, row k = k-th highest degree */
 int b200_get_window_table(void *plan, void *host_out);
 /* window Fourier series of dimension d, nf[d]/2+1 entries of the plan's real type */

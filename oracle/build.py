@@ -8,6 +8,9 @@
                           compiled where they lie under /root/reference with oracle/ref_shim.cpp
                           on top.  Only built when /root/reference exists (this container);
                           the GPU box uses the prebuilt file that travels with the snapshot.
+* oracle/_ref/libfinufft_ref_dirft.so — the REFERENCE's own direct sums and error norms
+                          (test/utils/dirft{1,2,3}d.hpp, norms.hpp) behind oracle/ref_dirft_shim.cpp:
+                          the direct-sum checker of every accuracy test.
 """
 import os
 import subprocess
@@ -54,6 +57,29 @@ def build_ref(force=False, verbose=False):
     return out
 
 
+def build_ref_dirft(force=False, verbose=False):
+    """The reference's own direct-sum checkers and norms (test/utils/dirft{1,2,3}d.hpp,
+    norms.hpp: dependency-free templates) compiled where they lie, with oracle/ref_dirft_shim.cpp
+    on top, into oracle/_ref/libfinufft_ref_dirft.so.  Returns the path or None."""
+    outdir = os.path.join(HERE, "_ref")
+    out = os.path.join(outdir, "libfinufft_ref_dirft.so")
+    shim = os.path.join(HERE, "ref_dirft_shim.cpp")
+    inc = os.path.join(REF, "test", "utils")
+    hdrs = [os.path.join(inc, f) for f in ("dirft1d.hpp", "dirft2d.hpp", "dirft3d.hpp",
+                                            "norms.hpp")]
+    if not all(os.path.exists(h) for h in hdrs):
+        return out if os.path.exists(out) else None
+    if force or _stale(out, [shim] + hdrs):
+        os.makedirs(outdir, exist_ok=True)
+        cmd = ["g++", "-std=c++17", "-O2", "-fopenmp", "-shared", "-fPIC", "-I", inc, shim,
+               "-o", out]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv, verbose=True))
     print(build_ref(force="--force" in sys.argv, verbose=True))
+    print(build_ref_dirft(force="--force" in sys.argv, verbose=True))

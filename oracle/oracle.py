@@ -60,6 +60,30 @@ def ref_lib():
     return r
 
 
+_ref_dirft = False
+
+
+def ref_dirft_lib():
+    """The reference's own test/utils/dirft*.hpp + norms.hpp compiled into oracle/_ref, or None."""
+    global _ref_dirft
+    if _ref_dirft is False:
+        path = os.path.join(HERE, "_ref", "libfinufft_ref_dirft.so")
+        if not os.path.exists(path):
+            try:
+                from . import build as _b
+                _b.build_ref_dirft()
+            except Exception:
+                pass
+        if os.path.exists(path):
+            r = C.CDLL(path)
+            r.ref_relerrtwonorm.restype = C.c_double
+            r.ref_relerrtwonorm.argtypes = [_i64, _p, _p]
+            _ref_dirft = r
+        else:
+            _ref_dirft = None
+    return _ref_dirft
+
+
 def _suf(dtype):
     dtype = np.dtype(dtype)
     if dtype in (np.float32, np.complex64):
@@ -332,9 +356,16 @@ class Plan:
 
 
 # ----------------------------------------------------------------------------- direct sums
-def dirft(type_, x, y, z, data, iflag, n_modes=None, s=None, t=None, u=None, nthr=0):
-    """Double-precision direct sums (test/utils/dirft{1,2,3}d.hpp semantics, CMCL order)."""
+def dirft(type_, x, y, z, data, iflag, n_modes=None, s=None, t=None, u=None, nthr=0, impl=None):
+    """Double-precision direct sums, CMCL mode order.  impl="ref": the reference's own
+    test/utils/dirft{1,2,3}d.hpp compiled into oracle/_ref (the default whenever that library is
+    present); impl="port": our restatement of them (orc_dirft*)."""
     nthr = nthr or max_threads()
+    rl = ref_dirft_lib() if impl in (None, "ref") else None
+    if impl == "ref" and rl is None:
+        raise RuntimeError("oracle/_ref/libfinufft_ref_dirft.so is not available")
+    L = rl if rl is not None else lib()
+    pre = "ref_" if rl is not None else "orc_"
     sign = 1 if iflag >= 0 else -1
     dim = 1 + (y is not None) + (z is not None)
     xs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z)]
@@ -345,24 +376,30 @@ def dirft(type_, x, y, z, data, iflag, n_modes=None, s=None, t=None, u=None, nth
               for a in (s, t, u)]
         nk = st[0].size
         out = np.zeros(nk, dtype=np.complex128)
-        lib().orc_dirft3(dim, _i64(M), _ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), _ptr(data), sign,
+        getattr(L, pre + "dirft3")(dim, _i64(M), _ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), _ptr(data), sign,
                          _i64(nk), _ptr(st[0]), _ptr(st[1]), _ptr(st[2]), _ptr(out), nthr)
         return out
     ms = np.array(list(n_modes) + [1] * (3 - dim), dtype=np.int64)
     if type_ == 1:
         out = np.zeros(int(np.prod(ms)), dtype=np.complex128)
-        lib().orc_dirft1(dim, _i64(M), _ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), _ptr(data), sign,
+        getattr(L, pre + "dirft1")(dim, _i64(M), _ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), _ptr(data), sign,
                          _ptr(ms), _ptr(out), nthr)
         return out
     out = np.zeros(M, dtype=np.complex128)
-    lib().orc_dirft2(dim, _i64(M), _ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), _ptr(out), sign,
+    getattr(L, pre + "dirft2")(dim, _i64(M), _ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), _ptr(out), sign,
                      _ptr(ms), _ptr(data), nthr)
     return out
 
 
 def relerr(a, b):
-    """||a-b||_2 / ||b||_2  (test/utils/norms.hpp relerrtwonorm)."""
+    """||a-b||_2 / ||b||_2, b = the trusted array: the reference's own relerrtwonorm
+    (test/utils/norms.hpp:17-37) when oracle/_ref holds it, else the same formula in numpy."""
     a = np.asarray(a).reshape(-1)
     b = np.asarray(b).reshape(-1)
+    rl = ref_dirft_lib()
+    if rl is not None and a.size == b.size and a.size > 0:
+        aa = np.ascontiguousarray(a, dtype=np.complex128)
+        bb = np.ascontiguousarray(b, dtype=np.complex128)
+        return float(rl.ref_relerrtwonorm(_i64(bb.size), _ptr(bb), _ptr(aa)))
     return float(np.linalg.norm(a.astype(np.complex128) - b.astype(np.complex128)) /
                  np.linalg.norm(b.astype(np.complex128)))

@@ -464,7 +464,7 @@ def test_type3_matches_oracle_and_direct_sum(cuda, oracle, prec, tol, dim):
     hp = F.HostPlan(3, dim, ntr, tol, 1, ct, upsampfac=2.0, allow_eps_too_small=1)
     hp.setpts(*pts, **dict(zip("stu", frq)))
     hgot = hp.execute(c)
-    assert oracle.relerr(hgot.reshape(-1), got.reshape(-1)) <= 1e-5 if prec == "f" else 1e-12
+    assert oracle.relerr(hgot.reshape(-1), got.reshape(-1)) <= (1e-5 if prec == "f" else 1e-12)
     # adjoint of type 3 (execute.hpp:515-545): targets -> sources with the conjugate kernel;
     # checked against the direct sum sum_k F_k exp(-i s_k.x_j) and the identity <F, A c> = <A^H F, c>
     F_in = _rand_c(rng, (ntr, N), ct)

@@ -194,3 +194,37 @@ def test_oracle_error_codes(oracle):
                        ((1e-20, 1, 1, 2.0, np.float64, False), 26)]:
         assert oracle.kernel_setup(*args)[0] == code
     assert oracle.kernel_setup(1e-9, 3, 1, 2.0, np.float32, True)[0] == 0
+
+
+def test_direct_sum_checker_is_the_reference_code(oracle):
+    """The direct-sum checker used by every accuracy test is the reference's own
+    test/utils/dirft{1,2,3}d.hpp + norms.hpp compiled into oracle/_ref; our restatement of them
+    (orc_dirft*) must agree with it to rounding, for every type and dimension."""
+    if oracle.ref_dirft_lib() is None:
+        pytest.skip("oracle/_ref/libfinufft_ref_dirft.so not present (no /root/reference)")
+    rng = np.random.default_rng(3)
+    M, nk = 300, 170
+    modes = {1: [37], 2: [12, 9], 3: [6, 7, 5]}
+    for dim in (1, 2, 3):
+        pts = [rng.uniform(-np.pi, np.pi, M) for _ in range(dim)] + [None] * (3 - dim)
+        frq = [rng.uniform(-30, 30, nk) for _ in range(dim)] + [None] * (3 - dim)
+        N = int(np.prod(modes[dim]))
+        c = rng.standard_normal(M) + 1j * rng.standard_normal(M)
+        f = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+        for sign in (+1, -1):
+            a = oracle.dirft(1, *pts, c, sign, n_modes=modes[dim], impl="ref")
+            b = oracle.dirft(1, *pts, c, sign, n_modes=modes[dim], impl="port")
+            assert oracle.relerr(b, a) < 1e-13
+            # one thread = the reference routine called once, untouched by the OpenMP driver
+            a1 = oracle.dirft(1, *pts, c, sign, n_modes=modes[dim], impl="ref", nthr=1)
+            assert oracle.relerr(a, a1) < 1e-13
+            a = oracle.dirft(2, *pts, f, sign, n_modes=modes[dim], impl="ref")
+            b = oracle.dirft(2, *pts, f, sign, n_modes=modes[dim], impl="port")
+            assert oracle.relerr(b, a) < 1e-13
+            a = oracle.dirft(3, *pts, c, sign, s=frq[0], t=frq[1], u=frq[2], impl="ref")
+            b = oracle.dirft(3, *pts, c, sign, s=frq[0], t=frq[1], u=frq[2], impl="port")
+            assert oracle.relerr(b, a) < 1e-12
+    # relerr itself is the reference's relerrtwonorm
+    u = rng.standard_normal(50) + 1j * rng.standard_normal(50)
+    v = u + 1e-3 * rng.standard_normal(50)
+    assert abs(oracle.relerr(v, u) - np.linalg.norm(v - u) / np.linalg.norm(u)) < 1e-15

@@ -1,17 +1,15 @@
 #!/bin/bash
-# parity tests + a few bench lines:  gpurun -- 'bash tools/gpu_quick.sh tag "c3_t2 c3_t1"'
-out=gpurun_out; mkdir -p $out
-tag=${1:-q}; wl=${2:-"c3_t1 c3_t2"}
-timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log
-tail -3 $out/${tag}_pytest.log
-for w in $wl; do
-  timeout 300 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > $out/${tag}_${w}.json 2> $out/${tag}_${w}.err
-  python - <<PY
-import json
-try:
-    d=json.loads(open("$out/${tag}_${w}.json").read().strip().splitlines()[-1])
-    print("$w", "ms/step %.3f"%d["ms_per_step"], {k: round(v,3) for k,v in d["stages_ms"].items()}, "setpts %.2f"%d["setpts_ms"], "e2e %.4g pts/s  %.2f ms"%(d["e2e"]["value"], d["e2e"]["ms_per_step"]))
-except Exception as e:
-    print("$w FAILED", e)
-PY
-done
+# Quick GPU visit: selected tests + one bench line.  gpurun --timeout 900 -- 'bash tools/gpu_quick.sh tag [pytest -k expr]'
+tag=${1:-q}
+kexpr=${2:-}
+out=gpurun_out
+mkdir -p $out
+if [ -n "$kexpr" ]; then
+  timeout 1200 python -m pytest tests -m gpu -x -q -s -k "$kexpr" > $out/${tag}_pytest.log 2>&1
+else
+  timeout 1500 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1
+fi
+echo "pytest exit $?" >> $out/${tag}_pytest.log
+tail -25 $out/${tag}_pytest.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu > $out/${tag}_bench_c3_t1.json 2> $out/${tag}_bench_c3_t1.err
+tail -c 2500 $out/${tag}_bench_c3_t1.json; tail -5 $out/${tag}_bench_c3_t1.err
