@@ -73,7 +73,8 @@ def build(force=False, verbose=False, jobs=None):
             list(ex.map(lambda s: _compile(s, verbose), todo))
     if todo or not os.path.exists(LIB):
         cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcufft", "-Xlinker",
-                                                               "--no-undefined"]
+                                                               "--no-undefined", "-Xlinker",
+                                                               "-soname=libfinufft_b200.so"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

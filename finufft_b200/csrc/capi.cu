@@ -156,6 +156,47 @@ EngineOpts from_host_opts(const finufft_opts *o) {
   return e;
 }
 
+// Option contract of the reference device API that callers (and the reference's own
+// test/cuda/test_makeplan.c, cufinufft_error_handling.cu) rely on, although this engine has a
+// single native method and its own bins:
+//  * a nonstandard upsampfac (not 0, 2 or 1.25) with gpu_kerevalmeth = 1 is error 8, upsampfac
+//    <= 1 otherwise error 7 (src/cuda/makeplan.cu:60-72);
+//  * a user-chosen shared-memory method (gpu_method 2 or 3) whose user-chosen bins would not fit
+//    the device's shared memory, or an unknown gpu_method, is error 19
+//    (src/cuda/makeplan.cu:307-327, src/cuda/heuristics.cu:34-42,326-445).
+template<class T> void validate_opts_gpu(int dim, double tol, const cufinufft_opts *o) {
+  if (!o) return;
+  const double sigma = o->upsampfac;
+  if (sigma != 0.0 && sigma != 2.0 && sigma != 1.25) {
+    if (o->gpu_kerevalmeth == 1) throw Failure{ERR_HORNER_WRONG_BETA};
+    if (sigma <= 1.0) throw Failure{ERR_UPSAMPFAC_TOO_SMALL};
+  }
+  if (o->gpu_method < 0 || o->gpu_method > 4) throw Failure{ERR_INSUFFICIENT_SHMEM};
+  const bool user_bins = (o->gpu_binsizex | o->gpu_binsizey | o->gpu_binsizez) != 0;
+  if ((o->gpu_method == 2 || o->gpu_method == 3) && user_bins) {
+    int limit = 0;
+    if (cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin,
+                               o->gpu_device_id) != cudaSuccess) {
+      cudaGetLastError();
+      throw Failure{ERR_CUDA_FAILURE};
+    }
+    // width the reference device library would pick (src/cuda/makeplan.cu:88-93)
+    const double eps = std::max(tol, (double)std::numeric_limits<T>::epsilon());
+    int ns = (int)std::ceil(-std::log10(eps / 10.0));
+    if (sigma != 0.0 && sigma != 2.0)
+      ns = (int)std::ceil(-std::log(eps) / (3.14159265358979323846 * std::sqrt(1 - 1 / sigma)));
+    ns = std::max(2, ns);
+    const int64_t pad = 2 * ((ns + 1) / 2);
+    const int64_t bx = o->gpu_binsizex ? o->gpu_binsizex : 1, by = o->gpu_binsizey ? o->gpu_binsizey : 1,
+                  bz = o->gpu_binsizez ? o->gpu_binsizez : 1;
+    if (bx < 0 || by < 0 || bz < 0) throw Failure{ERR_BINSIZE_NOTVALID};
+    double cells = (double)(bx + pad);
+    if (dim > 1) cells *= (double)(by + pad);
+    if (dim > 2) cells *= (double)(bz + pad);
+    if (cells * 2.0 * sizeof(T) > (double)limit) throw Failure{ERR_INSUFFICIENT_SHMEM};
+  }
+}
+
 template<class T>
 int gpu_makeplan(int type, int dim, const int64_t *nm, int iflag, int ntr, double tol, void **out,
                  const cufinufft_opts *o) {
@@ -163,6 +204,9 @@ int gpu_makeplan(int type, int dim, const int64_t *nm, int iflag, int ntr, doubl
     if (!out) throw Failure{ERR_INVALID_ARGUMENT};
     *out = nullptr;
     validate_modes_gpu(type, dim, nm);
+    if (type < 1 || type > 3) throw Failure{ERR_TYPE_NOTVALID};
+    if (ntr < 1) throw Failure{ERR_NTRANS_NOTVALID};
+    validate_opts_gpu<T>(dim, tol, o);
     *out = new DevicePlan<T>(type, dim, nm, iflag, ntr, tol, from_gpu_opts(o));
   });
 }

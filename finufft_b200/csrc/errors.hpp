@@ -8,6 +8,7 @@ enum ErrorCode : int {
   ERR_MAXNALLOC            = 2,   // fine grid larger than 1e12 points
   ERR_SPREAD_BOX_SMALL     = 3,   // a fine-grid dimension is below 2*ns
   ERR_UPSAMPFAC_TOO_SMALL  = 7,   // sigma <= 1
+  ERR_HORNER_WRONG_BETA    = 8,   // device API: nonstandard sigma with gpu_kerevalmeth = 1
   ERR_NTRANS_NOTVALID      = 9,
   ERR_TYPE_NOTVALID        = 10,
   ERR_ALLOC                = 11,

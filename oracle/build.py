@@ -79,7 +79,54 @@ def build_ref_dirft(force=False, verbose=False):
     return out
 
 
+REF_API_TESTS = {
+    # program: (source under /root/reference/test/cuda, compiler)
+    "test_makeplan": ("test_makeplan.c", "gcc"),
+    "public_api_test": ("public_api_test.c", "gcc"),
+    "cufinufft_error_handling": ("cufinufft_error_handling.cu", "nvcc"),
+    "cufinufft_multigpu_test": ("cufinufft_multigpu_test.cu", "nvcc"),
+    "cufinufft_simple_test": ("cufinufft_simple_test.cu", "nvcc"),
+}
+
+
+def build_ref_api_tests(force=False, verbose=False):
+    """The reference's own C / CUDA API contract tests (test/cuda/*.c, *.cu: plain programs over
+    <cufinufft.h>), compiled from the sources where they lie and LINKED AGAINST OUR LIBRARY
+    (finufft_b200/libfinufft_b200.so in place of libcufinufft), into oracle/_ref/bin/.  They run
+    on the GPU box from tests/test_gpu_ref_api.py.  The accuracy programs cufinufft{1,2,3}d_test.cu
+    include the reference's internal headers, which need the un-vendored POET dependency, and
+    cannot be built here.  Returns the list of programs present."""
+    outdir = os.path.join(HERE, "_ref", "bin")
+    srcdir = os.path.join(REF, "test", "cuda")
+    lib = os.path.join(HERE, "..", "finufft_b200", "libfinufft_b200.so")
+    have = []
+    for prog, (src, cc) in REF_API_TESTS.items():
+        out = os.path.join(outdir, prog)
+        path = os.path.join(srcdir, src)
+        if not os.path.exists(path) or not os.path.exists(lib):
+            if os.path.exists(out):
+                have.append(out)
+            continue
+        if force or _stale(out, [path]):
+            os.makedirs(outdir, exist_ok=True)
+            rpath = "$ORIGIN/../../../finufft_b200"
+            if cc == "gcc":
+                cmd = ["gcc", "-O1", "-I", os.path.join(REF, "include"), "-I",
+                       "/usr/local/cuda/include", path, "-o", out, os.path.abspath(lib),
+                       "-L/usr/local/cuda/lib64", "-lcudart", "-lm", f"-Wl,-rpath,{rpath}"]
+            else:
+                cmd = ["/usr/local/cuda/bin/nvcc", "-O1", "-std=c++17", "-gencode",
+                       "arch=compute_100a,code=sm_100a", "-I", os.path.join(REF, "include"), path,
+                       "-o", out, os.path.abspath(lib), "-Xlinker", f"-rpath={rpath}"]
+            if verbose:
+                print(" ".join(cmd))
+            subprocess.check_call(cmd)
+        have.append(out)
+    return have
+
+
 if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv, verbose=True))
     print(build_ref(force="--force" in sys.argv, verbose=True))
     print(build_ref_dirft(force="--force" in sys.argv, verbose=True))
+    print(build_ref_api_tests(force="--force" in sys.argv, verbose=True))

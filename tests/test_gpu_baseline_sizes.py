@@ -120,11 +120,15 @@ def test_c5_type3_f32(cuda, oracle):
                       s=frq[2][sel].astype(np.float64), t=frq[1][sel].astype(np.float64),
                       u=frq[0][sel].astype(np.float64))
     err_ds = oracle.relerr(got.reshape(-1)[sel], ds)
-    print(f"\n[type 3] gpu-vs-oracle {err:.3e}  gpu-vs-direct-sum(200 targets) {err_ds:.3e}")
-    # type 3 chains a spread, an inner type 2 and two phase multiplications: float noise of
-    # three stages; the reference's tolsweep bar for float type 3 is 5*tol with a 1e-5 floor
-    assert err <= max(2 * tol, 1e-5)
-    assert err_ds <= max(5 * tol, 1e-5)
+    floor_ds = oracle.relerr(want.reshape(-1)[sel], ds)   # what the CPU path itself reaches in f32
+    print(f"\n[type 3] gpu-vs-oracle {err:.3e}  gpu-vs-direct-sum(200 targets) {err_ds:.3e}  "
+          f"oracle-f32-vs-direct-sum (float floor) {floor_ds:.3e}")
+    # Bar vs the oracle: 2*tol.  Bar vs the direct sum: the reference's tolsweep rule for float
+    # type 3 (5*tol, floor 1e-5 at its small sizes); at this space-bandwidth product the phases
+    # s.x reach ~1e3 rad, so single precision itself limits any implementation to ~3e-5: the
+    # floor is measured with the CPU oracle in f32 on the same inputs and the gate follows it.
+    assert err <= 2 * tol
+    assert err_ds <= max(5 * tol, 1e-5, 1.5 * floor_ds)
     gp.destroy()
     op.destroy()
 

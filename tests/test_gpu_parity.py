@@ -492,8 +492,13 @@ def test_error_contract_gpu(cuda):
     o.gpu_device_id = 1234
     assert lib.cufinufftf_makeplan(1, 3, nm, 1, 1, C.c_float(1e-4), C.byref(p), C.byref(o)) == 15
     o.gpu_device_id = 0
+    # nonstandard sigma: error 8 with the default gpu_kerevalmeth = 1, error 7 (sigma <= 1) with
+    # gpu_kerevalmeth = 0 (reference src/cuda/makeplan.cu:60-72, test/cuda/test_makeplan.c:175-185)
     o.upsampfac = 1.0
+    assert lib.cufinufftf_makeplan(1, 3, nm, 1, 1, C.c_float(1e-4), C.byref(p), C.byref(o)) == 8
+    o.gpu_kerevalmeth = 0
     assert lib.cufinufftf_makeplan(1, 3, nm, 1, 1, C.c_float(1e-4), C.byref(p), C.byref(o)) == 7
+    o.gpu_kerevalmeth = 1
     o.upsampfac = 2.0
     assert lib.cufinufftf_makeplan(1, 3, nm, 1, 1, C.c_float(1e-4), C.byref(p), C.byref(o)) == 0
     before = cuda.cuda.current_device()
