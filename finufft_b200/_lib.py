@@ -60,6 +60,16 @@ class FinufftOpts(C.Structure):
     ]
 
 
+class SlabInfo(C.Structure):
+    _fields_ = [
+        ("is_float", C.c_int), ("type", C.c_int), ("rank", C.c_int), ("world", C.c_int),
+        ("ns", C.c_int), ("mode", C.c_int),
+        ("nf", C.c_int64 * 3), ("ms", C.c_int64 * 3),
+        ("z0", C.c_int64), ("nz", C.c_int64), ("ylo", C.c_int64), ("yhi", C.c_int64),
+        ("win_org", C.c_int64), ("win_n", C.c_int64), ("M", C.c_int64), ("M_local", C.c_int64),
+    ]
+
+
 class PlanInfo(C.Structure):
     _fields_ = [
         ("is_float", C.c_int), ("type", C.c_int), ("dim", C.c_int), ("ntr", C.c_int),
@@ -85,7 +95,11 @@ INTROSPECT = ["b200_get_plan_info", "b200_get_sort_permutation", "b200_get_raw_s
               "b200_get_phihat", "b200_enable_profiling", "b200_get_stage_ms",
               "b200_get_launch_count", "b200_host_kernel", "b200_host_fine_grid",
               "b200_host_fseries", "b200_version"]
-ALL_SYMBOLS = GURU_GPU + GURU_HOST + SIMPLE_GPU + SIMPLE_HOST + INTROSPECT
+SHARDED = ["b200_slab_unique_id", "b200_slab_get_info", "b200_slab_get_stage_ms",
+           "b200_slab_get_launch_count"] + [
+    f"b200_slab{p}_{n}" for p in ("", "f")
+    for n in ("makeplan", "setpts", "execute", "gather_modes", "slice_modes", "destroy")]
+ALL_SYMBOLS = GURU_GPU + GURU_HOST + SIMPLE_GPU + SIMPLE_HOST + INTROSPECT + SHARDED
 
 _lib = None
 
@@ -158,5 +172,28 @@ def load():
     lib.b200_host_fseries.argtypes = [i64, ci, ci, ci, vp, vp]
     lib.b200_host_fseries.restype = ci
     lib.b200_version.restype = C.c_char_p
+    lib.b200_slab_unique_id.argtypes = [vp]
+    lib.b200_slab_unique_id.restype = ci
+    for pre, real in (("", dbl), ("f", flt)):
+        mk = getattr(lib, f"b200_slab{pre}_makeplan")
+        mk.argtypes = [ci, C.POINTER(i64), ci, real, ci, ci, vp, C.POINTER(CufinufftOpts),
+                       C.POINTER(vp)]
+        mk.restype = ci
+        sp = getattr(lib, f"b200_slab{pre}_setpts")
+        sp.argtypes = [vp, i64, vp, vp, vp, ci]
+        sp.restype = ci
+        for nm in ("execute", "gather_modes", "slice_modes"):
+            f = getattr(lib, f"b200_slab{pre}_{nm}")
+            f.argtypes = [vp, vp, vp]
+            f.restype = ci
+        de = getattr(lib, f"b200_slab{pre}_destroy")
+        de.argtypes = [vp]
+        de.restype = ci
+    lib.b200_slab_get_info.argtypes = [vp, C.POINTER(SlabInfo)]
+    lib.b200_slab_get_info.restype = ci
+    lib.b200_slab_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 10)]
+    lib.b200_slab_get_stage_ms.restype = ci
+    lib.b200_slab_get_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.b200_slab_get_launch_count.restype = ci
     _lib = lib
     return lib

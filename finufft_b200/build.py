@@ -24,7 +24,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 EXPORT = ["-Xcompiler", "-fvisibility=default"]
 
 SOURCES = [
-    "planmath.cpp", "sort.cu", "partition.cu", "gridops.cu", "engine.cu", "sweep3d.cu", "stage.cu", "sweep2d_f32.cu", "sweep2d_f64.cu", "type3.cu", "capi.cu",
+    "planmath.cpp", "sort.cu", "partition.cu", "gridops.cu", "engine.cu", "sweep3d.cu", "stage.cu", "sweep2d_f32.cu", "sweep2d_f64.cu", "type3.cu", "slab.cu", "capi.cu", "capi_sharded.cu",
     "spreadinterp_f32_d1.cu", "spreadinterp_f32_d2.cu", "spreadinterp_f32_d3.cu",
     "spreadinterp_f64_d1.cu", "spreadinterp_f64_d2.cu", "spreadinterp_f64_d3.cu",
 ]
@@ -48,7 +48,7 @@ def _compile(src, verbose):
     obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
     path = os.path.join(CSRC, src)
     cmd = [NVCC] + ARCH + COMMON
-    if src == "capi.cu":
+    if src in ("capi.cu", "capi_sharded.cu"):
         cmd += EXPORT
     if src.endswith(".cpp"):
         cmd += ["-Xcompiler", "-ffp-contract=off", "-x", "cu"]
@@ -72,7 +72,7 @@ def build(force=False, verbose=False, jobs=None):
         with cf.ThreadPoolExecutor(max_workers=jobs or min(8, os.cpu_count() or 1)) as ex:
             list(ex.map(lambda s: _compile(s, verbose), todo))
     if todo or not os.path.exists(LIB):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcufft", "-Xlinker",
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcufft", "-ldl", "-Xlinker",
                                                                "--no-undefined", "-Xlinker",
                                                                "-soname=libfinufft_b200.so"]
         if verbose:

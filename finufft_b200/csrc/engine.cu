@@ -251,6 +251,14 @@ template<class T> void Engine<T>::plan_grid() {
   }
   if (nbins > 0x7fffffffull) throw Failure{ERR_NDATA_NOTVALID};
   geom.nbins = geom.nbins1 = (uint32_t)nbins;
+  geom.zwin_org = geom.zwin_n = 0;
+  if (opts.zwin_n > 0) {
+    if (dim != 3 || !opts.spreadinterponly || opts.zwin_n > nf[2] || opts.zwin_org < 0 ||
+        opts.zwin_org >= nf[2])
+      throw Failure{ERR_INVALID_ARGUMENT};
+    geom.zwin_org = opts.zwin_org;
+    geom.zwin_n   = opts.zwin_n == nf[2] ? 0 : opts.zwin_n;
+  }
   if (opts.spreadinterponly) return;
   if (type == 3) {  // spread grid only: the inner type-2 plan owns the FFT and the series
     fw_.alloc((size_t)total);

@@ -43,6 +43,9 @@ struct EngineOpts {
   int stage            = -1;    // two-level strength permutation (stage.cuh): -1 auto, 0 off, 1 on
   int check_sigma      = 0;     // host (finufft_*) entry points apply the CPU feasibility rule
   int partition        = 1;     // setpts: 1 partition sort where it pays, 2 always, 0 counting sort
+  // 3D spreadinterponly plans of a sharded transform (slab.cu): the grid handed to execute holds
+  // only zwin_n planes of the periodic grid, from global plane zwin_org (sort.cuh, GridGeom)
+  int zwin_org = 0, zwin_n = 0;
 };
 
 // Callbacks of a pipelined execute (host-pointer plans, capi.cu): the engine announces when it
@@ -98,7 +101,7 @@ template<class T> class Engine {
   GridGeom<T> geom{};
   uint32_t nsub = 0;
   int batch = 1;
-  int64_t grid_cells() const { return nf[0] * nf[1] * nf[2]; }
+  int64_t grid_cells() const { return nf[0] * nf[1] * (geom.zwin_n ? geom.zwin_n : nf[2]); }
   int64_t mode_count() const { return ms[0] * ms[1] * ms[2]; }
   // raw = false: the reference permutation (bins in order, ascending index inside a bin);
   // raw = true: the order the kernels work in

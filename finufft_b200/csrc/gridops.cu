@@ -19,23 +19,6 @@ namespace b200 {
 // x tile of kTileX cells; blockIdx.z = transform in the batch.
 constexpr int kRowsPerBlock = 8, kTileX = 2048, kGridThreads = 256;
 
-// mode index (0..ms-1 in storage order) -> signed frequency k
-__device__ __forceinline__ int mode_freq(int pos, int ms, int modeord) {
-  const int kmin = -(ms / 2), kmax = (ms - 1) / 2;
-  return modeord == 0 ? pos + kmin : (pos <= kmax ? pos : pos - ms);
-}
-// fine-grid cell -> signed frequency, false if the cell is outside the kept band
-__device__ __forceinline__ bool cell_freq(int cell, int ms, int nf, int &k) {
-  const int kmin = -(ms / 2), kmax = (ms - 1) / 2;
-  if (cell <= kmax) k = cell;
-  else if (cell >= nf + kmin) k = cell - nf;
-  else return false;
-  return true;
-}
-__device__ __forceinline__ int mode_pos(int k, int ms, int modeord) {
-  return modeord == 0 ? k + ms / 2 : (k >= 0 ? k : ms + k);
-}
-
 template<class T, int DIM>
 __global__ void __launch_bounds__(kGridThreads)
 k_grid_to_modes(const typename CxOf<T>::type *__restrict__ fw,

@@ -27,7 +27,21 @@ template<class T> struct GridGeom {
   uint32_t nbins1    = 0;  // bins of the grid = nb[0]*nb[1]*nb[2]
   uint32_t nchunks   = 1;
   uint32_t chunk_len = 0xffffffffu;
+  // z window (3D, sharded plans: slab.cu): the grid array holds only zwin_n consecutive planes
+  // of the periodic nf[2]-plane grid, starting at global plane zwin_org.  Folding, bins and
+  // stencils stay those of the whole grid; a cell of global plane P lives in array plane
+  // (P - zwin_org) mod nf[2], which must be < zwin_n for every cell a point of this plan
+  // touches.  zwin_n = 0: the array is the whole grid.
+  int zwin_org = 0, zwin_n = 0;
 };
+
+// array plane of global plane gz (already wrapped into [0, nf[2])), or -1 outside the window
+template<class T> __host__ __device__ __forceinline__ int grid_plane(const GridGeom<T> &g, int gz) {
+  if (g.zwin_n == 0) return gz;
+  int w = gz - g.zwin_org;
+  if (w < 0) w += g.nf[2];
+  return w < g.zwin_n ? w : -1;
+}
 
 // --- launchers (defined in sort.cu) -------------------------------------------------------
 template<class T>

@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(256) k_spread(const SpreadArgs<T, NS> a) {
   for (int r = 0; r < TL::PY * TL::PZ; ++r) {
     const int oy = r % TL::PY, oz = r / TL::PY;
     const int gy = DIM > 1 ? wrap_index(org2 + oy, nf2) : 0;
-    const int gz = DIM > 2 ? wrap_index(org3 + oz, nf3) : 0;
+    const int gz = DIM > 2 ? grid_plane(a.g, wrap_index(org3 + oz, nf3)) : 0;
+    if (gz < 0) continue;  // outside the z window: no point of this plan reaches it
     C *row        = a.fw + ((size_t)gz * nf2 + gy) * (size_t)nf1;
     const C *trow = tile + oy * TL::L + oz * TL::P;
     for (int ox = lane; ox < TL::PX; ox += 32) {
@@ -224,9 +225,13 @@ __global__ void __launch_bounds__(256) k_interp(const SpreadArgs<T, NS> a) {
   for (int r = 0; r < TL::PY * TL::PZ; ++r) {
     const int oy = r % TL::PY, oz = r / TL::PY;
     const int gy = DIM > 1 ? wrap_index(org2 + oy, nf2) : 0;
-    const int gz = DIM > 2 ? wrap_index(org3 + oz, nf3) : 0;
-    const C *row = a.fw + ((size_t)gz * nf2 + gy) * (size_t)nf1;
+    const int gz = DIM > 2 ? grid_plane(a.g, wrap_index(org3 + oz, nf3)) : 0;
     C *trow      = tile + oy * TL::L + oz * TL::P;
+    if (gz < 0) {  // outside the z window
+      for (int ox = lane; ox < TL::PX; ox += 32) trow[ox] = C{0, 0};
+      continue;
+    }
+    const C *row = a.fw + ((size_t)gz * nf2 + gy) * (size_t)nf1;
     for (int ox = lane; ox < TL::PX; ox += 32) trow[ox] = row[wrap_index(org1 + ox, nf1)];
   }
 

@@ -174,10 +174,12 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
 #pragma unroll
   for (int k = 0; k < CF::NRED; ++k) {
     const int yz = (lane + 32 * k) >> 1, z = yz / CF::YR, yc = yz - z * CF::YR;
-    const int gz = wrap_index(kBinZ * i3 - CF::HL + z, nf3),
+    const int gz = grid_plane(a.g, wrap_index(kBinZ * i3 - CF::HL + z, nf3)),
               gy = wrap_index(kBinY * i2 - CF::HL + yc, nf2);
-    lineoff[k] = z < CF::ZT ? ((uint32_t)gz * (uint32_t)nf2 + (uint32_t)gy) * (uint32_t)nf1
-                            : 0xffffffffu;
+    // planes outside a z window (sort.cuh) are never touched by this plan's points
+    lineoff[k] = z < CF::ZT && gz >= 0
+                     ? ((uint32_t)gz * (uint32_t)nf2 + (uint32_t)gy) * (uint32_t)nf1
+                     : 0xffffffffu;
   }
 
   // register window: x rows [jw, jw+8), this lane's row is x = la (mod 8); tile rows z = bq+4m
@@ -223,6 +225,8 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
     for (int k = 0; k < CF::NRED; ++k)
       if (lineoff[k] != 0xffffffffu)
         stage4[lane + 32 * k] = __ldg(reinterpret_cast<const float4 *>(a.fw + lineoff[k] + gx));
+      else if (lane + 32 * k < CF::ZT * CF::YR * (CF::SX / 2))
+        stage4[lane + 32 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
   };
   // spread: the window's first two x rows leave, their owners park them in staging.
