@@ -30,7 +30,7 @@ def _stale(target, sources):
 def build_oracle(force=False, verbose=False):
     src = os.path.join(HERE, "finufft_oracle.cpp")
     out = os.path.join(HERE, "liboracle.so")
-    if force or _stale(out, [src]):
+    if force or _stale(out, [src, os.path.join(HERE, "fft_standin.hpp")]):
         cmd = ["g++", "-std=c++17", "-O2", "-fno-fast-math", "-ffp-contract=off", "-fopenmp",
                "-shared", "-fPIC", src, "-o", out]
         if verbose:
@@ -76,6 +76,73 @@ def build_ref_dirft(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+    return out
+
+
+def build_ref_library(force=False, verbose=False):
+    """The reference's own CPU library (finufft[f]_makeplan / setpts / execute / destroy and the
+    simple interfaces): src/*.cpp, src/common/*.cpp and every include/finufft/*.hpp compiled
+    from where they lie under /root/reference, twice for the precision-specific sources (with
+    and without FINUFFT_SINGLE, src/CMakeLists.txt:17-34,80-82), with the reference's own
+    release flags (cmake/toolchain.cmake:12-24) and -mavx2 -mfma in place of -march=native so
+    the library also runs on the GPU box's host CPU.  Its three un-vendored third-party
+    dependencies are replaced by the stand-ins under oracle/shim/: xsimd (SIMD wrapper, lane
+    order only), POET (compile-time dispatch, no arithmetic) and FFTW (the FFT itself is then
+    oracle/fft_standin.hpp).  Sort, spread, interp, deconvolve, type-3 set-up and the guru
+    driver are the reference's code, unmodified.  -> oracle/_ref/libfinufft_ref.so or None."""
+    outdir = os.path.join(HERE, "_ref")
+    objdir = os.path.join(outdir, "obj")
+    out = os.path.join(outdir, "libfinufft_ref.so")
+    src = os.path.join(REF, "src")
+    shim = os.path.join(HERE, "shim")
+    per_prec = ["makeplan.cpp", "setpts.cpp", "execute.cpp", "spreadinterp.cpp",
+                "spreadinterp_1d.cpp", "spreadinterp_2d.cpp", "spreadinterp_3d.cpp"]
+    common = ["fft.cpp", "c_interface.cpp", "utils.cpp", "common/kernel.cpp", "common/pswf.cpp",
+              "common/utils.cpp"]
+    if not all(os.path.exists(os.path.join(src, f)) for f in per_prec + common):
+        return out if os.path.exists(out) else None
+    shims = [os.path.join(shim, f) for f in ("xsimd/xsimd.hpp", "poet/poet.hpp", "fftw3.h",
+                                             "fftw_standin.cpp")] + [
+        os.path.join(HERE, "fft_standin.hpp"), os.path.join(HERE, "ref_lib_shim.cpp")]
+    inc = os.path.join(REF, "include")
+    hdrs = [os.path.join(inc, "finufft", f) for f in os.listdir(os.path.join(inc, "finufft"))]
+    if not (force or _stale(out, shims + hdrs + [os.path.join(src, f) for f in per_prec + common])):
+        return out
+    os.makedirs(objdir, exist_ok=True)
+    flags = ["-std=c++17", "-O3", "-funroll-loops", "-ffp-contract=fast", "-fno-math-errno",
+             "-fno-signed-zeros", "-fno-trapping-math", "-fassociative-math", "-freciprocal-math",
+             "-fmerge-all-constants", "-ftree-vectorize", "-fimplicit-constexpr",
+             "-fcx-limited-range", "-fno-semantic-interposition", "-mavx2", "-mfma", "-fopenmp",
+             "-fPIC", "-fvisibility=hidden", "-DFINUFFT_NO_DEPRECATED_FIELDS", "-DFINUFFT_DLL",
+             "-Ddll_EXPORTS", "-I", shim, "-I", inc]
+    jobs = []
+    for f in per_prec:
+        jobs.append((os.path.join(src, f), os.path.join(objdir, f[:-4] + "_f64.o"), []))
+        jobs.append((os.path.join(src, f), os.path.join(objdir, f[:-4] + "_f32.o"),
+                     ["-DFINUFFT_SINGLE"]))
+    for f in common:
+        jobs.append((os.path.join(src, f),
+                     os.path.join(objdir, f.replace("/", "_")[:-4] + ".o"), []))
+    jobs.append((os.path.join(shim, "fftw_standin.cpp"), os.path.join(objdir, "fftw_standin.o"),
+                 []))
+    jobs.append((os.path.join(HERE, "ref_lib_shim.cpp"), os.path.join(objdir, "ref_lib_shim.o"),
+                 []))
+
+    def one(job):
+        s, o, extra = job
+        cmd = ["g++"] + flags + extra + ["-c", s, "-o", o]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        return o
+
+    import concurrent.futures as cf
+    with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(one, jobs))
+    cmd = ["g++", "-shared", "-fopenmp", "-o", out] + objs
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
     return out
 
 
@@ -129,4 +196,5 @@ if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv, verbose=True))
     print(build_ref(force="--force" in sys.argv, verbose=True))
     print(build_ref_dirft(force="--force" in sys.argv, verbose=True))
+    print(build_ref_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_ref_api_tests(force="--force" in sys.argv, verbose=True))

@@ -10,15 +10,21 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may load this library.  The product (finufft_b200/) never links or calls it.
 //
-// Parity status: the plan-time maths (ns, beta, PSWF, Horner fit, Gauss-Legendre,
-// next235) is pinned against the reference's own src/common/*.cpp compiled into
-// oracle/_ref (see oracle/ref_shim.cpp, tests/test_oracle_vs_ref.py) and against the
-// reference's known-answer table test/testutils.cpp:39-54.  The full reference CPU
-// library cannot be built here (needs xsimd/POET/FFTW|DUCC0 fetched from the network),
-// so spread/interp/deconvolve and the sort permutation are pinned to the reference
-// only through the reference tests' own criterion (direct-sum error thresholds of
-// test/tolsweep.cpp, mass conservation of test/spreadinterp1d_test.cpp): for those
-// functions bit-level parity is "unpinned" (no golden vectors exist in the reference).
+// Parity status: PINNED to the reference's own code run here.
+//  * Plan-time maths (ns, beta, PSWF, Horner fit, Gauss-Legendre, next235): against the
+//    reference's src/common/*.cpp compiled into oracle/_ref (oracle/ref_shim.cpp) and the
+//    known-answer table test/testutils.cpp:39-54.
+//  * Sort permutation, spread, interp, deconvolve, type-3 set-up, the guru driver: against
+//    oracle/_ref/libfinufft_ref.so = the reference's src/*.cpp + include/finufft/*.hpp
+//    compiled where they lie (oracle/build.py::build_ref_library), whose outputs are committed
+//    as tests/golden/reference_vectors.npz.  tests/test_reference_pin_cpu.py: permutation bit
+//    for bit, outputs to 1e-13 (double) / 5e-6 (single) relative l2, every golden case.
+//    The reference's three un-vendored third-party dependencies are replaced in that build by
+//    the stand-ins under oracle/shim/ (xsimd: SIMD wrapper, lane order only; POET: dispatch,
+//    no arithmetic; FFTW: the FFT below), so what is pinned is the reference's arithmetic up
+//    to SIMD summation order and FFT rounding - the same caveat the reference's own builds
+//    have between FFTW and DUCC0.
+//  * Direct sums: the reference's test/utils/dirft*.hpp (oracle/ref_dirft_shim.cpp).
 //
 // The FFT is a third-party dependency of the reference (FFTW 3.3.10 / ducc0_0_41_1,
 // CMakeLists.txt:73-76), absent from /root/reference; a plain mixed-radix (2,3,5)
@@ -36,6 +42,8 @@
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
+
+#include "fft_standin.hpp"
 #endif
 
 namespace orc {
@@ -835,88 +843,6 @@ void deconvolve(int dir, int dim, const i64 *ms, const i64 *nf, int modeord, con
 // FFT: unnormalised in-place complex DFT with exponent sign `sign`, sizes 2,3,5-smooth
 // (any size works, O(n*p) per prime factor p).  Stands in for FFTW/DUCC0
 // (src/fft.cpp:266-371; dims slowest-first, :253-261).
-template<class T> struct Fft1d {
-  i64 n;
-  int sign;
-  std::vector<std::complex<T>> tw;  // exp(sign*2*pi*i*k/n)
-  Fft1d(i64 n_, int sign_) : n(n_), sign(sign_), tw(n_) {
-    for (i64 k = 0; k < n; ++k) {
-      double ang = sign * 2.0 * PI * (double)k / (double)n;
-      tw[k]      = std::complex<T>((T)std::cos(ang), (T)std::sin(ang));
-    }
-  }
-  // out[0..m) = DFT of in[0], in[stride], ...  (length m, m | n)
-  void rec(i64 m, const std::complex<T> *in, i64 stride, std::complex<T> *out,
-           std::complex<T> *tmp) const {
-    if (m == 1) {
-      out[0] = in[0];
-      return;
-    }
-    int p = 0;
-    for (int cand : {4, 2, 3, 5})
-      if (m % cand == 0) { p = cand; break; }
-    if (!p) {
-      for (i64 cand = 7; cand <= m; cand += 2)
-        if (m % cand == 0) { p = (int)cand; break; }
-    }
-    const i64 q = m / p;
-    for (int r = 0; r < p; ++r) rec(q, in + r * stride, stride * p, tmp + r * q, out + r * q);
-    const i64 tstep = n / m;
-    if (p == 2) {
-      for (i64 k = 0; k < q; ++k) {
-        std::complex<T> a = tmp[k], b = tmp[q + k] * tw[k * tstep];
-        out[k]     = a + b;
-        out[k + q] = a - b;
-      }
-    } else if (p == 4) {
-      const std::complex<T> J(0, (T)sign);
-      for (i64 k = 0; k < q; ++k) {
-        std::complex<T> a = tmp[k], b = tmp[q + k] * tw[k * tstep],
-                        c = tmp[2 * q + k] * tw[2 * k * tstep],
-                        d = tmp[3 * q + k] * tw[3 * k * tstep];
-        std::complex<T> s0 = a + c, s1 = a - c, s2 = b + d, s3 = J * (b - d);
-        out[k]         = s0 + s2;
-        out[k + q]     = s1 + s3;
-        out[k + 2 * q] = s0 - s2;
-        out[k + 3 * q] = s1 - s3;
-      }
-    } else {
-      for (i64 k = 0; k < q; ++k)
-        for (int j = 0; j < p; ++j) {
-          const i64 kk = k + j * q;
-          std::complex<T> s = tmp[k];
-          for (int r = 1; r < p; ++r) s += tmp[r * q + k] * tw[((r * kk) % m) * tstep];
-          out[kk] = s;
-        }
-    }
-  }
-};
-template<class T> void fft_nd(int dim, const i64 *nf, int sign, T *data, int nthr) {
-  auto *a        = reinterpret_cast<std::complex<T> *>(data);
-  const i64 n[3] = {nf[0], dim > 1 ? nf[1] : 1, dim > 2 ? nf[2] : 1};
-  if (nthr < 1) nthr = 1;
-  for (int ax = 0; ax < dim; ++ax) {
-    const i64 len = n[ax];
-    Fft1d<T> plan(len, sign);
-    const i64 stride = (ax == 0) ? 1 : (ax == 1 ? n[0] : n[0] * n[1]);
-    const i64 nlines = n[0] * n[1] * n[2] / len;
-#pragma omp parallel num_threads(nthr)
-    {
-      std::vector<std::complex<T>> buf(len), out(len), tmp(len);
-#pragma omp for schedule(static)
-      for (i64 l = 0; l < nlines; ++l) {
-        i64 base;
-        if (ax == 0) base = l * n[0];
-        else if (ax == 1) base = (l / n[0]) * n[0] * n[1] + (l % n[0]);
-        else base = l;
-        for (i64 k = 0; k < len; ++k) buf[k] = a[base + k * stride];
-        plan.rec(len, buf.data(), 1, out.data(), tmp.data());
-        for (i64 k = 0; k < len; ++k) a[base + k * stride] = out[k];
-      }
-    }
-  }
-}
-
 // ----------------------------------------------------------------------------------
 // Plan object: the subset of FINUFFT_PLAN_T state the hot path needs
 // (include/finufft/plan.hpp:106-145) and the guru sequence makeplan / setpts / execute

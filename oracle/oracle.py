@@ -355,6 +355,164 @@ class Plan:
             pass
 
 
+# ----------------------------------------------------------------------------- the reference itself
+class _RefOpts(C.Structure):  # include/finufft_opts.h:32-71, field for field
+    _fields_ = [
+        ("modeord", C.c_int), ("spreadinterponly", C.c_int), ("debug", C.c_int),
+        ("spread_debug", C.c_int), ("showwarn", C.c_int), ("nthreads", C.c_int),
+        ("fftw", C.c_int), ("spread_sort", C.c_int), ("spread_kerevalmeth", C.c_int),
+        ("spread_kerpad", C.c_int), ("upsampfac", C.c_double), ("spread_thread", C.c_int),
+        ("maxbatchsize", C.c_int), ("spread_nthr_atomic", C.c_int),
+        ("spread_max_sp_size", C.c_int), ("spread_kerformula", C.c_int),
+        ("allow_eps_too_small", C.c_int), ("fftw_lock_fun", C.c_void_p),
+        ("fftw_unlock_fun", C.c_void_p), ("fftw_lock_data", C.c_void_p),
+    ]
+
+
+_ref_full = False
+
+
+def ref_full_lib():
+    """oracle/_ref/libfinufft_ref.so: the reference's own CPU library compiled where it lies
+    (oracle/build.py::build_ref_library), or None."""
+    global _ref_full
+    if _ref_full is False:
+        path = os.path.join(HERE, "_ref", "libfinufft_ref.so")
+        if not os.path.exists(path):
+            try:
+                from . import build as _b
+                _b.build_ref_library()
+            except Exception:
+                pass
+        _ref_full = C.CDLL(path) if os.path.exists(path) else None
+        if _ref_full is not None:
+            for pre, real in (("", C.c_double), ("f", C.c_float)):
+                mk = getattr(_ref_full, f"finufft{pre}_makeplan")
+                mk.argtypes = [C.c_int, C.c_int, C.POINTER(_i64), C.c_int, C.c_int, real,
+                               C.POINTER(_p), C.POINTER(_RefOpts)]
+                sp = getattr(_ref_full, f"finufft{pre}_setpts")
+                sp.argtypes = [_p, _i64, _p, _p, _p, _i64, _p, _p, _p]
+                for nm in ("execute", "execute_adjoint"):
+                    getattr(_ref_full, f"finufft{pre}_{nm}").argtypes = [_p, _p, _p]
+                getattr(_ref_full, f"finufft{pre}_destroy").argtypes = [_p]
+            for s in ("f32", "f64"):
+                f = getattr(_ref_full, f"ref_plan_perm_{s}")
+                f.restype = _i64
+                f.argtypes = [_p, _p, C.POINTER(C.c_int)]
+                f = getattr(_ref_full, f"ref_plan_phihat_{s}")
+                f.restype = _i64
+                f.argtypes = [_p, C.c_int, _p]
+                getattr(_ref_full, f"ref_plan_info_{s}").argtypes = [
+                    _p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                    C.POINTER(C.c_double), C.POINTER(_i64 * 3), C.POINTER(C.c_double)]
+    return _ref_full
+
+
+def have_reference():
+    return ref_full_lib() is not None
+
+
+class RefPlan:
+    """Guru plan of the REFERENCE CPU library (finufft[f]_makeplan / setpts / execute /
+    destroy, include/finufft/finufft_eitherprec.h:55-67), same Python surface as `Plan`."""
+
+    def __init__(self, type_, n_modes, iflag, ntr, tol, dtype, sigma=2.0, modeord=0,
+                 spread_only=False, allow_small=True, nthr=1, dim=None, spread_sort=1):
+        L = ref_full_lib()
+        if L is None:
+            raise RuntimeError("oracle/_ref/libfinufft_ref.so is not available")
+        self.L = L
+        self.s, self.rt, self.ct = _suf(dtype)
+        self.pre = "f" if self.s == "f32" else ""
+        self.type, self.ntr = type_, ntr
+        self.dim = len(n_modes) if dim is None else dim
+        nm = (_i64 * 3)(*(list(n_modes) + [1] * (3 - len(n_modes))))
+        self.n_modes = [int(nm[i]) for i in range(self.dim)]
+        o = _RefOpts()
+        getattr(L, f"finufft{self.pre}_default_opts")(C.byref(o))
+        o.upsampfac = sigma
+        o.modeord = modeord
+        o.spreadinterponly = int(spread_only)
+        o.allow_eps_too_small = int(allow_small)
+        o.nthreads = nthr
+        o.spread_sort = spread_sort
+        o.showwarn = 0
+        self.h = _p()
+        real = C.c_float if self.s == "f32" else C.c_double
+        err = getattr(L, f"finufft{self.pre}_makeplan")(type_, self.dim, nm, iflag, ntr,
+                                                        real(tol), C.byref(self.h), C.byref(o))
+        self.err = err
+        if err > 1:  # 1 = warning: eps too small, clamped (allow_eps_too_small)
+            self.h = None
+            raise RuntimeError(f"reference makeplan error {err}")
+        self._keep = None
+        self._info()
+
+    def _info(self):
+        ns, nc = C.c_int(), C.c_int()
+        beta, sigma, tol = C.c_double(), C.c_double(), C.c_double()
+        nf = (_i64 * 3)()
+        getattr(self.L, f"ref_plan_info_{self.s}")(self.h, C.byref(ns), C.byref(nc),
+                                                  C.byref(beta), C.byref(sigma), C.byref(nf),
+                                                  C.byref(tol))
+        self.ns, self.nc, self.beta, self.sigma, self.tol = (ns.value, nc.value, beta.value,
+                                                             sigma.value, tol.value)
+        self.nf = [int(nf[i]) for i in range(self.dim)]
+
+    def phihat(self, d):
+        n = getattr(self.L, f"ref_plan_phihat_{self.s}")(self.h, d, None)
+        out = np.zeros(n, dtype=self.rt)
+        getattr(self.L, f"ref_plan_phihat_{self.s}")(self.h, d, _ptr(out))
+        return out
+
+    def setpts(self, x, y=None, z=None, s=None, t=None, u=None, force_sort=True):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=self.rt)
+                for a in (x, y, z, s, t, u)]
+        self._keep = arrs  # the reference keeps the user's pointers (plan.hpp:130)
+        self.M = arrs[0].size
+        self.nk = 0 if arrs[3] is None else arrs[3].size
+        err = getattr(self.L, f"finufft{self.pre}_setpts")(
+            self.h, _i64(self.M), _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), _i64(self.nk),
+            _ptr(arrs[3]), _ptr(arrs[4]), _ptr(arrs[5]))
+        if err > 1:
+            raise RuntimeError(f"reference setpts error {err}")
+        self._info()
+
+    def perm(self):
+        did = C.c_int()
+        p = np.zeros(self.M, dtype=np.int64)
+        getattr(self.L, f"ref_plan_perm_{self.s}")(self.h, _ptr(p), C.byref(did))
+        self.did_sort = bool(did.value)
+        return p
+
+    def execute(self, data, adjoint=False):
+        data = np.ascontiguousarray(data, dtype=self.ct)
+        nm = int(np.prod(self.n_modes)) if self.type != 3 else self.nk
+        forward_in_c = (self.type != 2) != adjoint
+        if forward_in_c:
+            c = data.reshape(-1).copy()
+            fk = np.zeros(self.ntr * nm, dtype=self.ct)
+        else:
+            fk = data.reshape(-1).copy()
+            c = np.zeros(self.ntr * self.M, dtype=self.ct)
+        fn = getattr(self.L, f"finufft{self.pre}_execute" + ("_adjoint" if adjoint else ""))
+        err = fn(self.h, _ptr(c), _ptr(fk))
+        if err > 1:
+            raise RuntimeError(f"reference execute error {err}")
+        return fk if forward_in_c else c
+
+    def destroy(self):
+        if self.h is not None:
+            getattr(self.L, f"finufft{self.pre}_destroy")(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
 # ----------------------------------------------------------------------------- direct sums
 def dirft(type_, x, y, z, data, iflag, n_modes=None, s=None, t=None, u=None, nthr=0, impl=None):
     """Double-precision direct sums, CMCL mode order.  impl="ref": the reference's own

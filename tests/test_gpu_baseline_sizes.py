@@ -1,6 +1,8 @@
 """GPU parity at the BASELINE.json grid sizes: the CUDA path through the C ABI against the CPU
-oracle on identical inputs, with the number of points reduced so the oracle finishes in seconds
-(the grids, tolerances, precisions and kernel widths are the real ones).
+checker on identical inputs, with the number of points reduced so the checker finishes in
+seconds (the grids, tolerances, precisions and kernel widths are the real ones).  The checker is
+the REFERENCE CPU library itself (oracle/_ref/libfinufft_ref.so, oracle.RefPlan) whenever the
+snapshot carries it, else the restatement pinned to it (oracle.Plan).
 
 Bar (north_star): relative l2 error <= 2 x requested tolerance against the oracle in the same
 precision.  Two independent single-precision pipelines agree only down to their own rounding
@@ -28,8 +30,9 @@ def _run_pair(cuda, oracle, type_, modes, M, tol, rt, ct, kind, ntr=1, seed=5, f
     nf = gp.info()["nf"]
     pts = make_points(rng, dim, M, rt, kind, nf=nf[::-1])[:dim]
     gp.setpts(*[cuda.from_numpy(p).cuda() for p in pts])
-    op = oracle.Plan(type_, list(modes[::-1]), 1, ntr, tol, rt, sigma=2.0,
-                     nthr=oracle.max_threads())
+    Checker = oracle.RefPlan if oracle.have_reference() else oracle.Plan
+    op = Checker(type_, list(modes[::-1]), 1, ntr, tol, rt, sigma=2.0,
+                 nthr=oracle.max_threads())
     op.setpts(*(pts[::-1] + [None] * (3 - dim)))
     # bins are bit-exact: same permutation as the CPU's stable bin sort
     assert np.array_equal(gp.sort_permutation().astype(np.int64), op.perm())
@@ -40,14 +43,15 @@ def _run_pair(cuda, oracle, type_, modes, M, tol, rt, ct, kind, ntr=1, seed=5, f
     err = oracle.relerr(got, want)
     fl = 0.0
     if floor:
-        op64 = oracle.Plan(type_, list(modes[::-1]), 1, ntr, tol, np.float64, sigma=2.0,
-                           nthr=oracle.max_threads())
+        op64 = Checker(type_, list(modes[::-1]), 1, ntr, tol, np.float64, sigma=2.0,
+                       nthr=oracle.max_threads())
         op64.setpts(*[p.astype(np.float64) for p in pts[::-1]] + [None] * (3 - dim))
         want64 = op64.execute(data.astype(np.complex128))
         fl = oracle.relerr(want, want64)
         err64 = oracle.relerr(got, want64)
-        print(f"\n[{dim}D type {type_} {kind}] gpu-vs-oracle32 {err:.3e}  oracle32-vs-oracle64 "
-              f"(float floor) {fl:.3e}  gpu-vs-oracle64 {err64:.3e}")
+        who = "reference" if Checker is oracle.RefPlan else "oracle"
+        print(f"\n[{dim}D type {type_} {kind}] gpu-vs-{who}32 {err:.3e}  {who}32-vs-{who}64 "
+              f"(float floor) {fl:.3e}  gpu-vs-{who}64 {err64:.3e}")
         op64.destroy()
     gp.destroy()
     op.destroy()
