@@ -24,7 +24,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 EXPORT = ["-Xcompiler", "-fvisibility=default"]
 
 SOURCES = [
-    "planmath.cpp", "sort.cu", "partition.cu", "gridops.cu", "engine.cu", "sweep3d.cu", "stage.cu", "sweep2d_f32.cu", "sweep2d_f64.cu", "type3.cu", "slab.cu", "capi.cu", "capi_sharded.cu",
+    "planmath.cpp", "sort.cu", "partition.cu", "gridops.cu", "engine.cu", "sweep3d.cu", "stage.cu", "sweep2d_f32.cu", "sweep2d_f64.cu", "type3.cu", "direct.cu", "slab.cu", "capi.cu", "capi_sharded.cu",
     "spreadinterp_f32_d1.cu", "spreadinterp_f32_d2.cu", "spreadinterp_f32_d3.cu",
     "spreadinterp_f64_d1.cu", "spreadinterp_f64_d2.cu", "spreadinterp_f64_d3.cu",
 ]

@@ -132,6 +132,7 @@ EngineOpts from_gpu_opts(const cufinufft_opts *o) {
   e.debug            = d.debug;
   e.allow_eps_too_small = 1;  // the device API has no such switch; clamp and proceed
   e.check_sigma         = 0;
+  e.sort                = d.gpu_sort ? 1 : 0;  // include/cufinufft_opts.h:11
   return e;
 }
 
@@ -153,6 +154,11 @@ EngineOpts from_host_opts(const finufft_opts *o) {
   e.debug   = d.debug;
   e.allow_eps_too_small = d.allow_eps_too_small;
   e.check_sigma         = 1;
+  // include/finufft_opts.h:41: 0 don't sort, 1 sort, 2 heuristic choice.  The reference's
+  // heuristic (spreadinterp.hpp:161-163) skips the sort for 1D type 2 / tiny grids because a
+  // CPU thread streams such points well; on this device sorted points always win, so the
+  // library's own choice for 2 is to sort.
+  e.sort = d.spread_sort == 0 ? 0 : 1;
   return e;
 }
 

@@ -382,6 +382,29 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
   if (dim > 1) ys_.alloc(M);
   if (dim > 2) zs_.alloc(M);
   sidx_.alloc(M);
+  unsorted_ = opts.sort == 0 && type != 3;
+  if (unsorted_) {
+    // the caller asked for no sort: identity permutation (reference indexSort,
+    // spreadinterp.hpp:186-191), coordinates kept as given, point-driven kernels at execute
+    geom.nchunks = 1, geom.chunk_len = 0xffffffffu, geom.nbins = geom.nbins1;
+    swept_ = swept2_ = staged_ = radix_order_ = part_used_ = false;
+    nsub = 0, nitems_ = 0;
+    group_sub_.assign(2, 0);
+    group_item_.assign(2, 0);
+    if (M) {
+      launch_iota(sidx_.p, m, st);
+      CU(cudaMemcpyAsync(xs_.p, x, sizeof(T) * M, cudaMemcpyDeviceToDevice, st));
+      if (dim > 1) CU(cudaMemcpyAsync(ys_.p, y, sizeof(T) * M, cudaMemcpyDeviceToDevice, st));
+      if (dim > 2) CU(cudaMemcpyAsync(zs_.p, z, sizeof(T) * M, cudaMemcpyDeviceToDevice, st));
+    }
+    if (!coef_dev_.p) {
+      coef_dev_.alloc(coef.size());
+      CU(cudaMemcpyAsync(coef_dev_.p, coef.data(), sizeof(T) * coef.size(),
+                         cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return;
+  }
   binstart_.alloc((size_t)geom.nbins + 1);
   const size_t scan_n = std::max<size_t>(geom.nbins + 1, 256 * (size_t)kRadixMaxBlocks + 1);
   Scratch<uint32_t> scan_tmp(scan_n / 4096 + 8, st, dev);
@@ -578,6 +601,13 @@ cudaError_t Engine<T>::sweep_run(bool spread, C *c, C *fw, const uint32_t *ix, u
 }
 // group = -1: all points; else the work items / subproblems of that point group only
 template<class T> void Engine<T>::run_spread(const C *c, C *fw, int group) {
+  if (unsorted_) {
+    if (group > 0) return;  // one group only
+    CU(launch_direct<T>(true, dim, ns, nc, coef_dev_.p, xs_.p, ys_.p, zs_.p, (uint32_t)M, geom, c,
+                        nullptr, fw, opts.stream));
+    if (M) ++launches;
+    return;
+  }
   if (nsub == 0) return;
   uint32_t s0 = 0, s1 = nsub, it0 = 0, it1 = nitems_;
   if (group >= 0) {
@@ -612,6 +642,13 @@ template<class T> void Engine<T>::run_spread(const C *c, C *fw, int group) {
   ++launches;
 }
 template<class T> void Engine<T>::run_interp(C *c, const C *fw, int group) {
+  if (unsorted_) {
+    if (group > 0) return;
+    CU(launch_direct<T>(false, dim, ns, nc, coef_dev_.p, xs_.p, ys_.p, zs_.p, (uint32_t)M, geom,
+                        nullptr, c, const_cast<C *>(fw), opts.stream));
+    if (M) ++launches;
+    return;
+  }
   if (nsub == 0) return;
   uint32_t s0 = 0, s1 = nsub, it0 = 0, it1 = nitems_;
   if (group >= 0) {
@@ -761,7 +798,7 @@ void Engine<T>::execute(C *c, C *fk, bool adjoint, const ExecHooks *hooks) {
 template<class T> void Engine<T>::copy_sort_to_host(uint32_t *out, bool raw) const {
   if (M == 0) return;
   cudaStream_t st = opts.stream;
-  if (raw || radix_order_) {  // the device order as it stands
+  if (raw || radix_order_ || unsorted_) {  // the device order as it stands
     cudaStreamSynchronize(st);
     cuda_check(cudaMemcpy(out, sidx_.p, sizeof(uint32_t) * M, cudaMemcpyDeviceToHost), "copy sort");
     return;

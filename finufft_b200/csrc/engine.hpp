@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "devmath.cuh"
+#include "direct.cuh"
 #include "errors.hpp"
 #include "gridops.cuh"
 #include "sort.cuh"
@@ -43,6 +44,10 @@ struct EngineOpts {
   int stage            = -1;    // two-level strength permutation (stage.cuh): -1 auto, 0 off, 1 on
   int check_sigma      = 0;     // host (finufft_*) entry points apply the CPU feasibility rule
   int partition        = 1;     // setpts: 1 partition sort where it pays, 2 always, 0 counting sort
+  // bin sort at setpts: 1 sort, 0 keep the user's order and run the point-driven kernels
+  // (direct.cuh), 2 = library's choice (this engine: sort).  gpu_sort / spread_sort of the
+  // reference's option structs (include/cufinufft_opts.h:11, include/finufft_opts.h:41)
+  int sort             = 1;
   // 3D spreadinterponly plans of a sharded transform (slab.cu): the grid handed to execute holds
   // only zwin_n planes of the periodic grid, from global plane zwin_org (sort.cuh, GridGeom)
   int zwin_org = 0, zwin_n = 0;
@@ -106,7 +111,9 @@ template<class T> class Engine {
   // raw = false: the reference permutation (bins in order, ascending index inside a bin);
   // raw = true: the order the kernels work in
   void copy_sort_to_host(uint32_t *out, bool raw = false) const;
-  int sort_path() const { return radix_order_ ? 2 : (part_used_ ? 1 : 0); }
+  // 0 counting sort, 1 partition sort, 2 stable radix sort, 3 not sorted (identity order)
+  int sort_path() const { return unsorted_ ? 3 : (radix_order_ ? 2 : (part_used_ ? 1 : 0)); }
+  bool did_sort() const { return !unsorted_; }
   void copy_phihat_to_host(int d, T *out) const;
   cudaStream_t stream() const { return opts.stream; }
   // stage timing (CUDA events on the plan's stream) and launch accounting for benches
@@ -166,6 +173,8 @@ template<class T> class Engine {
   bool radix_order_ = false;  // sidx_ is the reference permutation as it stands
   bool part_used_   = false;  // the last setpts took the partition sort (partition.cuh)
   bool pool_held_   = false;
+  bool unsorted_    = false;  // the last setpts kept the user's order (opts.sort = 0)
+  DevBuf<T> coef_dev_;        // polynomial table for the point-driven kernels
   // type 3
   DevBuf<T> xp_[3], sp_[3];
   DevBuf<C> prephase_, deconv_, cp_, ck_;

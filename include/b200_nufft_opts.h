@@ -20,7 +20,7 @@
 typedef struct cufinufft_opts {
   double upsampfac;         /* [used] sigma; 0 = choose (2.0) */
   int gpu_method;           /* ignored: one method only */
-  int gpu_sort;             /* ignored: points are always bin-sorted */
+  int gpu_sort;             /* 1 bin-sort at setpts, 0 keep the user's order (point-driven kernels) */
   int gpu_binsizex;         /* ignored: bins are the CPU library's 16 x 4 x 4 */
   int gpu_binsizey;
   int gpu_binsizez;
@@ -49,7 +49,7 @@ typedef struct finufft_opts {
   int showwarn;             /* [used] warnings on stderr */
   int nthreads;             /* ignored: no host threading */
   int fftw;                 /* ignored: cuFFT */
-  int spread_sort;          /* ignored: always sorted */
+  int spread_sort;          /* 0 keep the user's order, 1 sort, 2 library's choice (= sort) */
   int spread_kerevalmeth;   /* ignored */
   int spread_kerpad;        /* ignored */
   double upsampfac;         /* [used] 0 = choose (2.0) */
