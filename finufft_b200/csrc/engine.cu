@@ -9,6 +9,8 @@
 
 #include <mutex>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "partition.cuh"
 #include "planmath.hpp"
 #include "scratch.hpp"
@@ -87,6 +89,9 @@ template struct DevBuf<float2>;
 template struct DevBuf<double2>;
 template struct DevBuf<uint32_t>;
 template struct DevBuf<SweepItem>;
+
+NvtxRange::NvtxRange(const char *name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 DeviceGuard::DeviceGuard(int dev) {
   int count = 0;
@@ -571,6 +576,7 @@ void Engine<T>::setpts(int64_t M_, const T *x, const T *y, const T *z, int64_t N
   }
   for (int d = 0; d < dim; ++d)
     if (nf[d] < 2 * ns) throw Failure{ERR_SPREAD_BOX_SMALL};
+  NvtxRange range("b200::setpts (fold + bin sort)");
   mark(4);
   sort_points(x, y, z);
   mark(5);
@@ -704,6 +710,8 @@ void Engine<T>::spread_path(C *c, C *fk, int fsign, const ExecHooks *hooks) {
     C *grid      = opts.spreadinterponly ? fk + (int64_t)b0 * Nm : fw_.p;
     order_[0] = 0, order_[1] = 1, order_[2] = 2;
     mark(0);
+    {
+    NvtxRange range("b200::spread");
     CU(cudaMemsetAsync(grid, 0, sizeof(C) * (size_t)G * nb, st));
     const int ngrp = (int)geom.nchunks;
     for (int i = 0; i < nb; ++i) {
@@ -718,6 +726,7 @@ void Engine<T>::spread_path(C *c, C *fk, int fsign, const ExecHooks *hooks) {
         run_spread(cv, gv, ngrp == 1 ? -1 : k);
       }
     }
+    }
     mark(1);
     if (opts.spreadinterponly) {
       mark(2);
@@ -725,8 +734,12 @@ void Engine<T>::spread_path(C *c, C *fk, int fsign, const ExecHooks *hooks) {
       if (hooks && hooks->after_modes) hooks->after_modes(b0, nb);
       continue;
     }
-    fft_grid(fw_.p, nb, fsign, true);
+    {
+      NvtxRange range("b200::fft (cuFFT)");
+      fft_grid(fw_.p, nb, fsign, true);
+    }
     mark(2);
+    NvtxRange range("b200::deconvolve");
     launch_grid_to_modes<T>(dim, nb, fw_.p, fk + (int64_t)b0 * Nm, mg, st);
     ++launches;
     mark(3);
@@ -758,13 +771,20 @@ void Engine<T>::interp_path(C *c, C *fk, int fsign, const ExecHooks *hooks) {
       mark(1);
       mark(2);
     } else {
-      launch_modes_to_grid<T>(dim, nb, fk + (int64_t)b0 * Nm, fw_.p, mg, st);
+      {
+        NvtxRange range("b200::amplify");
+        launch_modes_to_grid<T>(dim, nb, fk + (int64_t)b0 * Nm, fw_.p, mg, st);
+      }
       ++launches;
       mark(1);
-      fft_grid(fw_.p, nb, fsign, false);
+      {
+        NvtxRange range("b200::fft (cuFFT)");
+        fft_grid(fw_.p, nb, fsign, false);
+      }
       mark(2);
     }
     const int ngrp = (int)geom.nchunks;
+    NvtxRange range("b200::interp");
     for (int i = 0; i < nb; ++i) {
       C *cv       = c + (int64_t)(b0 + i) * M;
       const C *gv = grid + (int64_t)i * G;

@@ -73,6 +73,13 @@ template<class T> struct DevBuf {
   void release();
 };
 
+// NVTX range for the duration of a scope (visible in Nsight Systems / Compute timelines; a no-op
+// without a tool attached).  Header-only NVTX 3: no link dependency.
+struct NvtxRange {
+  explicit NvtxRange(const char *name);
+  ~NvtxRange();
+};
+
 struct DeviceGuard {  // make the plan's device current for the duration of a call
   int prev = -1;
   explicit DeviceGuard(int dev);

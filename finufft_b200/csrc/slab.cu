@@ -607,6 +607,7 @@ void SlabPlan<T>::setpts(int64_t M_, const T *x, const T *y, const T *z, int rou
   if (M_ < 0) throw Failure{ERR_NUM_NU_PTS_INVALID};
   if (M_ > std::numeric_limits<int32_t>::max()) throw Failure{ERR_NDATA_NOTVALID};
   M = M_;
+  NvtxRange range("b200::slab setpts (route + sort)");
   mark(9);
   const int nf3 = (int)nf[2];
   const int dev = opts.device;
@@ -809,6 +810,7 @@ template<class T> void SlabPlan<T>::route_values(bool to_owner, C *user) {
 // ------------------------------------------------------------------ execute
 template<class T> void SlabPlan<T>::execute(C *c, C *fk_block) {
   DeviceGuard guard(opts.device);
+  NvtxRange range(type == 1 ? "b200::slab execute (type 1)" : "b200::slab execute (type 2)");
   if (!eng_) throw Failure{ERR_PLAN_NOTVALID};
   SlabGeom g{};
   for (int d = 0; d < 3; ++d) g.ms[d] = (int)ms[d], g.nf[d] = (int)nf[d];

@@ -431,6 +431,10 @@ cudaError_t launch_spread3_sweep(int ns, const SweepPoints &pts, const GridGeom<
                                  const float *coef, const float2 *c_in, float2 *fw,
                                  cudaStream_t st) {
   switch (ns) {
+  case 2: return launch_ns<2, true>(pts, g, nc, coef, c_in, nullptr, fw, st);
+  case 3: return launch_ns<3, true>(pts, g, nc, coef, c_in, nullptr, fw, st);
+  case 4: return launch_ns<4, true>(pts, g, nc, coef, c_in, nullptr, fw, st);
+  case 5: return launch_ns<5, true>(pts, g, nc, coef, c_in, nullptr, fw, st);
   case 6: return launch_ns<6, true>(pts, g, nc, coef, c_in, nullptr, fw, st);
   case 7: return launch_ns<7, true>(pts, g, nc, coef, c_in, nullptr, fw, st);
   default: return cudaErrorInvalidValue;
@@ -440,11 +444,14 @@ cudaError_t launch_spread3_sweep(int ns, const SweepPoints &pts, const GridGeom<
 cudaError_t launch_interp3_sweep(int ns, const SweepPoints &pts, const GridGeom<float> &g, int nc,
                                  const float *coef, float2 *c_out, const float2 *fw,
                                  cudaStream_t st) {
+  float2 *g_ = const_cast<float2 *>(fw);
   switch (ns) {
-  case 6:
-    return launch_ns<6, false>(pts, g, nc, coef, nullptr, c_out, const_cast<float2 *>(fw), st);
-  case 7:
-    return launch_ns<7, false>(pts, g, nc, coef, nullptr, c_out, const_cast<float2 *>(fw), st);
+  case 2: return launch_ns<2, false>(pts, g, nc, coef, nullptr, c_out, g_, st);
+  case 3: return launch_ns<3, false>(pts, g, nc, coef, nullptr, c_out, g_, st);
+  case 4: return launch_ns<4, false>(pts, g, nc, coef, nullptr, c_out, g_, st);
+  case 5: return launch_ns<5, false>(pts, g, nc, coef, nullptr, c_out, g_, st);
+  case 6: return launch_ns<6, false>(pts, g, nc, coef, nullptr, c_out, g_, st);
+  case 7: return launch_ns<7, false>(pts, g, nc, coef, nullptr, c_out, g_, st);
   default: return cudaErrorInvalidValue;
   }
 }

@@ -275,6 +275,55 @@ def test_sweep2d_stage_parity_all_widths(cuda, oracle, kind):
     assert {n for p_, n in seen if p_ == "d"} >= set(range(3, 16))
 
 
+@pytest.mark.parametrize("kind", ["uniform", "cluster", "edges"])
+def test_sweep3d_stage_parity_all_widths(cuda, oracle, kind):
+    """3D single-precision row-sweep kernels (sweep3d.cu), spread-only and interp-only, for every
+    width they are built for (ns = 2..7) against the oracle's spread / interp on the same
+    points and against the generic kernels (B200_NUFFT_SWEEP=0); wider kernels (sigma = 1.25
+    at tight tolerance) must land on the generic kernels and still match."""
+    import finufft_b200 as F
+    rng = np.random.default_rng(57)
+    grid, M = (28, 36, 48), 40_000
+    seen = set()
+    for tol, sigma in [(3e-1, 2.0), (3e-2, 2.0), (3e-3, 2.0), (3e-4, 2.0), (3e-5, 2.0),
+                       (1e-6, 2.0), (1e-3, 1.25), (1e-5, 1.25), (1e-6, 1.25)]:
+        rt, ct = np.float32, np.complex64
+        err, ns, beta, tolu = oracle.kernel_setup(tol, 3, 1, sigma, rt, True)
+        assert err == 0
+        seen.add(ns)
+        coef, _ = oracle.horner(ns, beta, tolu, rt)
+        pts = make_points(rng, 3, M, rt, kind, nf=grid)
+        lp = pts[::-1]
+        perm, _ = oracle.bin_sort(lp[0], lp[1], lp[2], list(grid[::-1]))
+        c = _rand_c(rng, (M,), ct)
+        g = _rand_c(rng, grid, ct)
+        want_s = oracle.spread(list(grid[::-1]), lp[0], lp[1], lp[2], c, perm, coef)
+        want_i = oracle.interp(list(grid[::-1]), lp[0], lp[1], lp[2], g.reshape(-1), perm, coef)
+        bar = 3e-6 if kind == "uniform" else 3e-5
+        dpts = [cuda.from_numpy(p).cuda() for p in pts]
+        res = {}
+        for sweep in ("1", "0"):
+            os.environ["B200_NUFFT_SWEEP"] = sweep
+            try:
+                sp = F.Plan(1, grid, 1, tol, 1, ct, upsampfac=sigma, gpu_spreadinterponly=1)
+                sp.setpts(*dpts)
+                assert sp.info()["ns"] == ns
+                fw = sp.execute(cuda.from_numpy(c).cuda()).cpu().numpy()
+                ip = F.Plan(2, grid, 1, tol, 1, ct, upsampfac=sigma, gpu_spreadinterponly=1)
+                ip.setpts(*dpts)
+                ci = ip.execute(cuda.from_numpy(g).cuda()).cpu().numpy()
+            finally:
+                os.environ.pop("B200_NUFFT_SWEEP", None)
+            assert oracle.relerr(fw, want_s) < bar, (ns, sigma, sweep, "spread")
+            assert oracle.relerr(ci, want_i) < bar, (ns, sigma, sweep, "interp")
+            res[sweep] = (fw, ci)
+            sp.destroy()
+            ip.destroy()
+        assert oracle.relerr(res["1"][0], res["0"][0]) < bar, (ns, sigma, "spread")
+        assert oracle.relerr(res["1"][1], res["0"][1]) < bar, (ns, sigma, "interp")
+    assert seen >= set(range(2, 8)), seen
+
+
 def test_sweep2d_ragged_and_batched(cuda, oracle):
     """Few points (fewer than a chunk, one point, none), many vectors, odd grid sizes."""
     import finufft_b200 as F

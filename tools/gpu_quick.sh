@@ -11,5 +11,7 @@ else
 fi
 echo "pytest exit $?" >> $out/${tag}_pytest.log
 tail -25 $out/${tag}_pytest.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu > $out/${tag}_bench_c3_t1.json 2> $out/${tag}_bench_c3_t1.err
+timeout 600 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench_c3_t1.json 2> $out/${tag}_bench_c3_t1.err
 tail -c 2500 $out/${tag}_bench_c3_t1.json; tail -5 $out/${tag}_bench_c3_t1.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
+tail -c 1500 $out/${tag}_bench_reference.json; tail -5 $out/${tag}_bench_reference.err
