@@ -8,7 +8,11 @@ with no data-path collective.  Only if the caller wants every rank to hold the f
 one all_gather issued at the end (NCCL over NVLink on GPUs, gloo in the CPU tests).
 
 The single-large-transform case (z-slab decomposition of the fine grid with ghost-plane
-exchange and a distributed FFT) is the next row; it is not built yet.
+exchange and a distributed FFT) is `finufft_b200.sharded.ShardedPlan`, which
+binds the C++ / NCCL implementation behind include/b200_sharded.h.
+
+`bench.py --workload c4_t1 --gpus N` runs this split on the BASELINE batched config (2D f64,
+512^2 modes, M = 1e7, ntransf = 64).
 """
 from typing import Callable, List, Tuple
 

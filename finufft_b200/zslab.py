@@ -1,4 +1,13 @@
-"""One large 3D type-1 / type-2 transform sharded across the GPUs of one box by z-slabs of the
+"""HOST-SIDE MODEL of the z-slab decomposition, kept for the CPU tests only.
+
+The product path is csrc/slab.cu behind include/b200_sharded.h (python: finufft_b200.sharded.
+ShardedPlan): C++ driving the library's own kernels, cuFFT and NCCL.  This module restates the
+same decomposition with torch.distributed collectives and an injectable local spreader, so that
+tests/test_zslab_gloo_cpu.py can check the exchange logic (ghost planes, slab<->pencil
+transpose, mode blocks, deconvolution factors) on CPU with the `gloo` backend and the oracle
+as the local spreader.  Nothing in bench.py or the GPU tests uses it.
+
+One large 3D type-1 / type-2 transform sharded across the GPUs of one box by z-slabs of the
 fine grid.  One process per GPU; `torch.distributed` (NCCL over NVLink on
 GPUs, gloo in the CPU tests) carries the two exchange steps the path really has:
 
