@@ -5,9 +5,9 @@ kexpr=${2:-}
 out=gpurun_out
 mkdir -p $out
 if [ -n "$kexpr" ]; then
-  timeout 1200 python -m pytest tests -m gpu -x -q -s -k "$kexpr" > $out/${tag}_pytest.log 2>&1
+  timeout 1200 python -m pytest tests -m gpu -q -s -k "$kexpr" > $out/${tag}_pytest.log 2>&1
 else
-  timeout 1500 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1
+  timeout 1500 python -m pytest tests -m gpu -q > $out/${tag}_pytest.log 2>&1
 fi
 echo "pytest exit $?" >> $out/${tag}_pytest.log
 tail -25 $out/${tag}_pytest.log
