@@ -33,8 +33,7 @@ template<int NS> struct SweepCfg {
   static constexpr int RECW = 36;                   // words per point record
   // record: [0,NS) phi_y  [7] key (window position << 4 | jb)  [8,16) phi_x rotated so that
   //         word 8+a is the weight of the window row x = a (mod 8)  [16+4*bq+m] phi_z of tile
-  //         row bq+4m, [16+4*bq+3] = mask of the row groups m the stencil reaches (the same for
-  //         every bq)  [32,33] strength (spread)
+  //         row bq+4m  [32,33] strength (spread)
   static constexpr size_t STAGE_BYTES = (size_t)NRED * 32 * sizeof(float4);
   static constexpr size_t REC_BYTES   = (size_t)(CH + 2) * RECW * sizeof(float);
   static constexpr int PP = 17;  // pitch of a point's 16 partial sums (odd: conflict-free rows)
@@ -95,17 +94,10 @@ __device__ __forceinline__ void make_record(const SweepArgs<NS> &a, const RawPoi
   eval_window_t(a.tab, x1, kv);
   // z stencil start relative to the tile's first z row, in [0, kBinZ]
   const int k0 = min(max(i0 - (kBinZ * i3 - CF::HL), 0), kBinZ);
-  // tile row z = k0 + t lives in word 16 + 4*(z & 3) + (z >> 2).  Row group m (tile rows
-  // 4m..4m+3, one per lane group) holds a non-zero weight for some lane only if it meets the
-  // stencil rows [k0, k0+NS): the mask lets the warp skip the groups that are all zero.
-  int zmask = 0;
-#pragma unroll
-  for (int m = 0; m < CF::RZ; ++m)
-    if (4 * m <= k0 + NS - 1 && 4 * m + 3 >= k0) zmask |= 1 << m;
-  const float zmf = __int_as_float(zmask);
+  // tile row z = k0 + t lives in word 16 + 4*(z & 3) + (z >> 2)
 #pragma unroll
   for (int bq = 0; bq < CF::BQ; ++bq)
-    *reinterpret_cast<float4 *>(rec + 16 + 4 * bq) = make_float4(0.f, 0.f, 0.f, zmf);
+    *reinterpret_cast<float4 *>(rec + 16 + 4 * bq) = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int t = 0; t < NS; ++t) rec[16 + 4 * ((k0 + t) & 3) + ((k0 + t) >> 2)] = kv[t];
   *reinterpret_cast<float2 *>(rec + 32) = c;
@@ -115,12 +107,11 @@ __device__ __forceinline__ void make_record(const SweepArgs<NS> &a, const RawPoi
 struct LaneRec {
   float4 k0, k1;  // phi_y[0..6], key
   float wx;       // phi_x of this lane's window row
-  float4 fz;      // phi_z of this lane's tile rows; .w = mask of the live row groups
+  float4 fz;      // phi_z of this lane's tile rows
   float2 c;       // strength (spread only)
 };
 
-// RM = mask of the row groups to update (the others carry zero weights for this point)
-template<int NS, int JB, int RM>
+template<int NS, int JB>
 __device__ __forceinline__ void spread_update(float2 (&acc)[SweepCfg<NS>::RZ][SweepCfg<NS>::YR],
                                               const LaneRec &r) {
   using CF = SweepCfg<NS>;
@@ -129,14 +120,13 @@ __device__ __forceinline__ void spread_update(float2 (&acc)[SweepCfg<NS>::RZ][Sw
   const float2 cw   = fmul2_s(r.wx, r.c);
 #pragma unroll
   for (int m = 0; m < CF::RZ; ++m) {
-    if (!(RM & (1 << m))) continue;
     const float2 w = fmul2_s(fz[m], cw);
 #pragma unroll
     for (int t = 0; t < NS; ++t) acc[m][JB + t] = ffma2_s(ky[t], w, acc[m][JB + t]);
   }
 }
 // this lane's share of one point's interpolated value
-template<int NS, int JB, int RM>
+template<int NS, int JB>
 __device__ __forceinline__ float2 interp_gather(
     const float2 (&gv)[SweepCfg<NS>::RZ][SweepCfg<NS>::YR], const LaneRec &r) {
   using CF = SweepCfg<NS>;
@@ -145,7 +135,6 @@ __device__ __forceinline__ float2 interp_gather(
   float2 tot = make_float2(0.f, 0.f);
 #pragma unroll
   for (int m = 0; m < CF::RZ; ++m) {
-    if (!(RM & (1 << m))) continue;
     // one chain per row (splitting it in two was measured slower: the extra packed add per row
     // costs more FMA-pipe time than the shorter dependency chain saves)
     float2 s = fmul2_s(ky[0], gv[m][JB]);
@@ -373,33 +362,20 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
       const int key = __float_as_int(nx.k1.w);
       if (key < 0) break;
       advance_to(2 * (key >> 4) - CF::XB);
-// one point: the mask of live row groups is warp-uniform (every lane reads the same word)
-#define B200_POINT(J, R, P)                                                         \
-  {                                                                                 \
-    const int zm = __float_as_int((R).fz.w);                                        \
-    if (CF::RZ == 3 && zm == 3) {                                                   \
-      if (SPREAD) spread_update<NS, J, 3>(acc, (R));                                \
-      else put_part((P), interp_gather<NS, J, 3>(acc, (R)));                        \
-    } else if (CF::RZ == 3 && zm == 6) {                                            \
-      if (SPREAD) spread_update<NS, J, 6>(acc, (R));                                \
-      else put_part((P), interp_gather<NS, J, 6>(acc, (R)));                        \
-    } else {                                                                        \
-      if (SPREAD) spread_update<NS, J, (1 << CF::RZ) - 1>(acc, (R));                \
-      else put_part((P), interp_gather<NS, J, (1 << CF::RZ) - 1>(acc, (R)));        \
-    }                                                                               \
-  }
 #define B200_RUN(J)                                                 \
   case J:                                                           \
     for (;;) {                                                      \
       LaneRec n2 = load(p + 1);                                     \
-      B200_POINT(J, nx, p)                                          \
+      if (SPREAD) spread_update<NS, J>(acc, nx);                    \
+      else put_part(p, interp_gather<NS, J>(acc, nx));              \
       if (__float_as_int(n2.k1.w) != key) {                         \
         nx = n2;                                                    \
         p += 1;                                                     \
         break;                                                      \
       }                                                             \
       nx = load(p + 2);                                             \
-      B200_POINT(J, n2, p + 1)                                      \
+      if (SPREAD) spread_update<NS, J>(acc, n2);                    \
+      else put_part(p + 1, interp_gather<NS, J>(acc, n2));          \
       p += 2;                                                       \
       if (__float_as_int(nx.k1.w) != key) break;                    \
     }                                                               \
@@ -409,7 +385,6 @@ __global__ void __launch_bounds__(32, 16) k_sweep3(const SweepArgs<NS> a) {
       default: __builtin_unreachable();
       }
 #undef B200_RUN
-#undef B200_POINT
     }
     __syncwarp();
     if (!SPREAD && lane < nc) {  // lane = point: add its 16 partial sums, scatter
