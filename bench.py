@@ -411,6 +411,7 @@ def main():
         # stage breakdown (max over ranks per stage), separate pass
         stage = {}
         for i in range(5):
+            barrier()  # the first exchange of a step would otherwise absorb the ranks' skew
             sp.execute(data[i & 1], out)
             for k, v in sp.stage_ms().items():
                 stage.setdefault(k, []).append(v)

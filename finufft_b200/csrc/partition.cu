@@ -92,10 +92,18 @@ k_bin_hist(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict
       if (DIM > 2) pz = __ldcs(z + i);
     }
     const uint32_t key = valid ? bin_key_of<T, DIM>(px, py, pz, i, g) : 0xffffffffu;
-    // one RED per distinct bin in the warp (clustered input: one per warp instead of 32
-    // serialised on one address)
-    const uint32_t peers = __match_any_sync(0xffffffffu, key);
-    if (valid && lane == __ffs(peers) - 1) atomicAdd(&cnt[key], (uint32_t)__popc(peers));
+    // Clustered input: one RED per distinct bin in the warp instead of up to 32 serialised on one
+    // address (match_any).  Spread-out input never has two lanes in one bin, and match_any is
+    // the most expensive instruction of the loop (short-scoreboard stalls, profiles/
+    // r2g_setpts_ncu.txt), so it runs only when a cheap neighbour test sees a repeated bin.
+    const bool twin = key == __shfl_xor_sync(0xffffffffu, key, 1) ||
+                      key == __shfl_xor_sync(0xffffffffu, key, 2);
+    if (!__any_sync(0xffffffffu, twin && valid)) {
+      if (valid) atomicAdd(&cnt[key], 1u);
+    } else {
+      const uint32_t peers = __match_any_sync(0xffffffffu, key);
+      if (valid && lane == __ffs(peers) - 1) atomicAdd(&cnt[key], (uint32_t)__popc(peers));
+    }
   }
 }
 
@@ -134,8 +142,10 @@ template<class T> struct PartCfg {
                                  (size_t)TILE * sizeof(uint16_t);
 };
 
+// two resident blocks per SM (<= 64 registers): the pass is latency-bound between its barriers,
+// measured 25 % warp occupancy with one 100-register block (profiles/r2g_setpts_ncu.txt)
 template<class T, int DIM, bool RAW>
-__global__ void __launch_bounds__(PartCfg<T>::THREADS)
+__global__ void __launch_bounds__(PartCfg<T>::THREADS, 2)
 k_part(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
        const Packed4<T> *__restrict__ rin, uint32_t M, GridGeom<T> g, int ss, int shift,
        uint32_t *__restrict__ cursor, Packed4<T> *__restrict__ rout) {
@@ -376,12 +386,16 @@ static bool partition_sort_dim(const T *x, const T *y, const T *z, uint32_t M,
 
   using PC = PartCfg<T>;
   Scratch<Packed4<T>> recB(M, st, device);
-  const int nblk = (int)std::min<uint64_t>(((uint64_t)M + PC::TILE - 1) / PC::TILE, 148ull * 2);
+  const int nblk = (int)std::min<uint64_t>(((uint64_t)M + PC::TILE - 1) / PC::TILE, 148ull * 4);
   {  // per device, so on every call (cheap)
     cu(cudaFuncSetAttribute(k_part<T, DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)PC::SMEM));
     cu(cudaFuncSetAttribute(k_part<T, DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)PC::SMEM));
+    cu(cudaFuncSetAttribute(k_part<T, DIM, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    cu(cudaFuncSetAttribute(k_part<T, DIM, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
     cu(cudaFuncSetAttribute(k_seg_sort<T, DIM, kClassNone>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SegCfg<T>::SMEM));
     cu(cudaFuncSetAttribute(k_seg_sort<T, DIM, kClassSweep3>,

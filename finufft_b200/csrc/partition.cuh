@@ -16,7 +16,7 @@
 // to the algorithmic 2.8 GB (the <= 1024 write frontiers merge in the L2).  So:
 //
 //   1. k_bin_hist      bins counted with warp-aggregated REDs          -> scan -> binstart
-//   2. k_seg_prep      segments = 2^ss consecutive bins (~2700 points): cursors, largest segment
+//   2. k_seg_prep      segments = 2^ss consecutive bins (~1400 points): cursors, largest segment
 //   3. k_part (level A) raw coordinates -> records grouped by the high digit of the segment
 //   4. k_part (level B) records -> records grouped by segment          (skipped if <= 1024 segments)
 //   5. k_seg_sort      one block per segment: shared-memory counting sort by (bin, window
@@ -36,7 +36,7 @@ namespace b200 {
 
 constexpr int kPartFanout = 1024;  // digit values one partition pass separates
 template<class T> struct SegCap {  // most points of one segment
-  static constexpr uint32_t value = sizeof(T) == 4 ? 4096 : 2048;
+  static constexpr uint32_t value = sizeof(T) == 4 ? 2048 : 1024;  // 4 resident sort blocks per SM
 };
 
 // window classes of the sweep kernels (how the points of one bin are ordered)

@@ -357,6 +357,7 @@ k_route_fill(const T *__restrict__ x, const T *__restrict__ y, const T *__restri
       for (int w = 0; w < 8; ++w) tot += wcnt[w][threadIdx.x];
       base_[threadIdx.x] += tot;
     }
+    __syncthreads();  // wcnt is cleared at the top of the next round
   }
 }
 

@@ -13,12 +13,13 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1c"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2g"
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 for f in glob.glob(os.path.join(G, f"{tag}_bench_*.json")) + glob.glob(os.path.join(G, f"{tag}_bench_*.txt")):
     shutil.copy(f, P)
-for f in (f"{tag}_pytest_gpu.log", f"{tag}_launches_c3_t1.csv"):
+for f in (f"{tag}_pytest_gpu.log", f"{tag}_launches_c3_t1.csv", f"{tag}_launches_setpts.csv",
+          f"{tag}_smi.txt"):
     if os.path.exists(os.path.join(G, f)):
         shutil.copy(os.path.join(G, f), P)
 
@@ -29,6 +30,14 @@ for k in ("sweep_spread", "sweep_interp", "sweep2_spread", "sweep2_interp"):
         out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, "1e8"],
                              capture_output=True, text=True).stdout
         open(os.path.join(P, f"{tag}_{k}_ncu.txt"), "w").write(out.replace(G + "/", "gpurun_out/"))
+
+
+rep = os.path.join(G, f"{tag}_setpts.ncu-rep")
+if os.path.exists(rep):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_digest.py"), rep],
+                         capture_output=True, text=True).stdout
+    open(os.path.join(P, f"{tag}_setpts_ncu.txt"), "w").write(
+        f"# ncu --set full of the setpts kernels at C3 (gpurun_out/{tag}_setpts.ncu-rep)\n" + out)
 
 
 def raw(rep):
@@ -73,7 +82,8 @@ if os.path.exists(lc):
     tot = sp + fft + dc
     bench = json.loads(open(os.path.join(G, f"{tag}_bench_c3_t1.json")).read().strip().splitlines()[-1])
     st = bench["stages_ms"]
-    setp = {k: sum(v) / len(v) for k, v in ms.items() if k.startswith(("k_bin_count", "k_bin_place", "k_refine"))}
+    setp = {k: sum(v) / len(v) for k, v in ms.items()
+            if k.startswith(("k_bin_hist", "k_part", "k_seg_sort", "k_bin_count", "k_bin_place", "k_refine"))}
     txt = f"""# {tag}: ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --no-cpu`
 # (profiles/{tag}_launches_c3_t1.csv; per-launch times are cold-cache/serialised: the SHARE of the step counts)
 # one device-resident execute of C3 type 1 = memset(fw) + k_sweep3<7,1> + cuFFT kernels (pruned 3D) + k_grid_to_modes
@@ -82,7 +92,7 @@ k_sweep3<7,1> (spread)     {sp:.3f}            {100 * sp / tot:.1f} %
 cuFFT (all kernels)        {fft:.3f}            {100 * fft / tot:.1f} %
 k_grid_to_modes<float,3>   {dc:.3f}            {100 * dc / tot:.1f} %
 # bench.py stages_ms (CUDA events, same run family): spreadinterp {st['spreadinterp']:.3f} (incl. 0.17 ms memset), fft {st['fft']:.3f}, deconv {st['deconv']:.3f}
-# the e2e leg (finufft_execute, host pointers) spreads in 4 point groups: {len(grp)} k_sweep3 launches of {min(grp or [0]):.2f}..{max(grp or [0]):.2f} ms
+# the e2e leg (finufft_execute, host pointers) spreads in 4 point groups: {len(grp)} k_sweep3 launches of {min(grp or [0]):.2f}..{max(grp or [0]):.2f} ms (and the type-2 side leg's interp launches)
 # setpts (once per point set): """ + ", ".join(f"{k} {v:.3f}" for k, v in setp.items()) + "\n"
     open(os.path.join(P, f"{tag}_launch_shares.txt"), "w").write(txt)
     print(txt)

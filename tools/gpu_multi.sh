@@ -15,3 +15,5 @@ for wl in c3_t1 c3_t2; do
 done
 timeout 600 $TR bench.py --gpus $n --steps 10 --warmup 3 --workload c3_t1 --dist cluster --no-extras > $out/${tag}_bench_c3_t1_cluster_g$n.json 2> $out/${tag}_bench_c3_t1_cluster_g$n.err
 tail -c 2500 $out/${tag}_bench_c3_t1_cluster_g$n.json; tail -5 $out/${tag}_bench_c3_t1_cluster_g$n.err
+timeout 900 $TR bench.py --gpus $n --steps 5 --warmup 3 --workload c4_t1 --no-cpu > $out/${tag}_bench_c4_t1_g$n.json 2> $out/${tag}_bench_c4_t1_g$n.err
+tail -c 1500 $out/${tag}_bench_c4_t1_g$n.json; tail -5 $out/${tag}_bench_c4_t1_g$n.err

@@ -38,4 +38,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sw
   -o $out/${tag}_sweep2_interp python tools/prof_run.py --workload c2_t2 --reps 1 > $out/${tag}_ncu_full_interp2.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sweep2 -c 1 -f \
   -o $out/${tag}_sweep2_spread python tools/prof_run.py --workload c2_t1 --reps 1 > $out/${tag}_ncu_full_spread2.log 2>&1
+# setpts kernels: one full capture each (first launch of k_part = raw pass, second = record pass)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_part|k_seg_sort|k_bin_hist" -c 4 -f \
+  -o $out/${tag}_setpts python tools/prof_run.py --workload c3_t1 --reps 1 > $out/${tag}_ncu_full_setpts.log 2>&1
 ls -la $out | tail -40
