@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfinufft_b200.so")
+# B200_NUFFT_LIBRARY: development hook (kernel-variant A/B probes); unset in normal use
+LIB_PATH = os.environ.get("B200_NUFFT_LIBRARY") or os.path.join(HERE, "libfinufft_b200.so")
 
 
 class CufinufftOpts(C.Structure):

@@ -333,10 +333,16 @@ static uint32_t sweep2_item_points() {
   const long v  = e ? atol(e) : 0;
   return v >= 32 ? (uint32_t)v : kSweep2ItemPoints;
 }
-static uint32_t sweep3_item_points() {
+// Most points one warp of the 3D sweep kernels takes: a whole row of bins when the point set is
+// large (each item pays one window start and one final flush), smaller pieces when the set is
+// small (a rank's share of a sharded transform), so that the 148 x 16 resident warps get at
+// least ~6 waves of items and the last wave does not dominate.
+static uint32_t sweep3_item_points(uint64_t M) {
   const char *e = getenv("B200_SWEEP3_ITEM");
   const long v  = e ? atol(e) : 0;
-  return v >= 32 ? (uint32_t)v : kSweepItemPoints;
+  if (v >= 32) return (uint32_t)v;
+  const uint64_t want = M / (148ull * 16 * 6);
+  return (uint32_t)std::min<uint64_t>(kSweepItemPoints, std::max<uint64_t>(1024, want));
 }
 // refined order inside the bins for the sweep kernels; work units = 512-point chunks of bins
 static void refine_impl(int ns, const Packed4<float> *packed, float *xs, float *ys, float *zs,
@@ -538,7 +544,7 @@ template<class T> void Engine<T>::build_sweep_items(uint32_t *scan_tmp) {
   const uint32_t nrows1 = (uint32_t)geom.nb[1] * (uint32_t)geom.nb[2];
   const uint32_t nrows  = nrows1 * geom.nchunks;  // rows are group-major like the bins
   Scratch<uint32_t> nit(nrows, st, dev), itstart((size_t)nrows + 1, st, dev);
-  const uint32_t maxpts = swept2_ ? sweep2_item_points() : sweep3_item_points();
+  const uint32_t maxpts = swept2_ ? sweep2_item_points() : sweep3_item_points((uint64_t)M);
   launch_row_item_count(binstart_.p, nrows, (uint32_t)geom.nb[0], maxpts, nit.p, st);
   exclusive_scan_u32(nit.p, itstart.p, nrows, scan_tmp, st);
   uint32_t total = 0;

