@@ -137,6 +137,59 @@ k_slab_pack(const C *__restrict__ own, C *__restrict__ send, SlabGeom g) {
   }
 }
 
+// Peer-memory forms (slab.hpp): the same crop / zero-pad, but the rows are stored into (type 1)
+// or loaded from (type 2) the pencil arrays of the ranks that own their y range, over NVLink.
+// Pencil of rank r: [z global][y in r's range][x].
+template<class C> struct PeerPtrs {
+  C *p[kMaxWorld];
+};
+template<class C>
+__global__ void __launch_bounds__(kThreads)
+k_slab_pack_peer(const C *__restrict__ own, PeerPtrs<C> pencil, SlabGeom g, int z0) {
+  const int nrows = g.nz * g.ms[1];
+  for (int i = 0; i < kRows; ++i) {
+    const int row = blockIdx.x * kRows + i;
+    if (row >= nrows) return;
+    // rows of one destination are consecutive: py fastest inside a plane
+    const int py = row % g.ms[1], zl = row / g.ms[1];
+    const int ky = mode_freq(py, g.ms[1], g.modeord);
+    const int r  = y_owner(g, py);
+    const int ylen = g.ystart[r + 1] - g.ystart[r];
+    const C *srow  = own + ((int64_t)zl * g.nf[1] + (ky >= 0 ? ky : g.nf[1] + ky)) * g.nf[0];
+    C *drow = pencil.p[r] + ((int64_t)(z0 + zl) * ylen + (py - g.ystart[r])) * g.ms[0];
+    for (int px = threadIdx.x; px < g.ms[0]; px += kThreads) {
+      const int kx = mode_freq(px, g.ms[0], g.modeord);
+      drow[px]     = srow[kx >= 0 ? kx : g.nf[0] + kx];
+    }
+  }
+}
+template<class C, class T>
+__global__ void __launch_bounds__(kThreads)
+k_slab_unpack_peer(PeerPtrs<C> pencil, C *__restrict__ own, SlabGeom g, int z0) {
+  const int nrows = g.nz * g.nf[1];
+  for (int i = 0; i < kRows; ++i) {
+    const int row = blockIdx.x * kRows + i;
+    if (row >= nrows) return;
+    const int cy = row % g.nf[1], zl = row / g.nf[1];
+    C *drow = own + (int64_t)row * g.nf[0];
+    int ky  = 0;
+    if (!cell_freq(cy, g.ms[1], g.nf[1], ky)) {
+      for (int cx = threadIdx.x; cx < g.nf[0]; cx += kThreads) drow[cx] = C{(T)0, (T)0};
+      continue;
+    }
+    const int py   = mode_pos(ky, g.ms[1], g.modeord);
+    const int r    = y_owner(g, py);
+    const int ylen = g.ystart[r + 1] - g.ystart[r];
+    const C *srow  = pencil.p[r] + ((int64_t)(z0 + zl) * ylen + (py - g.ystart[r])) * g.ms[0];
+    for (int cx = threadIdx.x; cx < g.nf[0]; cx += kThreads) {
+      int kx = 0;
+      C v    = C{(T)0, (T)0};
+      if (cell_freq(cx, g.ms[0], g.nf[0], kx)) v = srow[mode_pos(kx, g.ms[0], g.modeord)];
+      drow[cx] = v;
+    }
+  }
+}
+
 // type 2, after the transpose: the mirror image, zero-padding the planes to nf2 x nf1
 template<class C, class T>
 __global__ void __launch_bounds__(kThreads)
@@ -361,6 +414,28 @@ k_route_fill(const T *__restrict__ x, const T *__restrict__ y, const T *__restri
   }
 }
 
+// Routing over peer memory: send position pos (destination-major, k_route_fill) belongs to rank
+// d = the block of `sendoff` holding it; its slot in d's array is peer_off[d] + pos - sendoff[d].
+// push: strengths of the caller's points are stored into the owners' arrays (type 1);
+// pull: interpolated values are loaded from them (type 2).
+struct RouteTable {
+  int world;
+  uint32_t sendoff[kMaxWorld + 1];
+  uint32_t peer_off[kMaxWorld];
+};
+template<class C, bool PUSH>
+__global__ void k_route_peer(C *__restrict__ user, const uint32_t *__restrict__ order,
+                             PeerPtrs<C> owner, RouteTable t, uint32_t n) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += stride) {
+    int d = 0;
+    while (d + 1 < t.world && pos >= t.sendoff[d + 1]) ++d;
+    C *slot = owner.p[d] + (t.peer_off[d] + (pos - t.sendoff[d]));
+    if (PUSH) *slot = user[order[pos]];
+    else user[order[pos]] = *slot;
+  }
+}
+
 template<class C>
 __global__ void k_gather_by(const C *__restrict__ src, const uint32_t *__restrict__ order,
                             C *__restrict__ dst, uint32_t n) {
@@ -476,6 +551,15 @@ SlabPlan<T>::SlabPlan(int type_, const int64_t *nmodes, int iflag, double tol_, 
 
 template<class T> SlabPlan<T>::~SlabPlan() {
   cudaStreamSynchronize(st_);
+  if (!opened_.empty() || p2p_) {
+    // no rank may free a buffer another rank still has mapped: unmap, then meet (collective)
+    close_peers();
+    try {
+      barrier();
+    } catch (...) {
+    }
+    cudaStreamSynchronize(st_);
+  }
   eng_.reset();
   if (comm_) nccl().CommDestroy((ncclComm_t)comm_);
   if (have2_) cufftDestroy(fft2_);
@@ -579,6 +663,10 @@ void SlabPlan<T>::route_points(const T *x, const T *y, const T *z) {
   }
   Ml = (int64_t)recvoff_[world];
   if (Ml > std::numeric_limits<int32_t>::max()) throw Failure{ERR_NDATA_NOTVALID};
+  // where this rank's block starts inside rank d's received array: the blocks of ranks < rank
+  peer_off_.assign(world, 0);
+  for (int d = 0; d < world; ++d)
+    for (int s = 0; s < rank; ++s) peer_off_[d] += mat[(size_t)s * world + d];
   xr_.alloc(std::max<size_t>(1, Ml));
   yr_.alloc(std::max<size_t>(1, Ml));
   zr_.alloc(std::max<size_t>(1, Ml));
@@ -609,6 +697,12 @@ void SlabPlan<T>::setpts(int64_t M_, const T *x, const T *y, const T *z, int rou
   if (M_ > std::numeric_limits<int32_t>::max()) throw Failure{ERR_NDATA_NOTVALID};
   M = M_;
   NvtxRange range("b200::slab setpts (route + sort)");
+  if (!opened_.empty() || p2p_) {  // buffers may be reallocated below: unmap everywhere first
+    CU(cudaStreamSynchronize(st_));
+    close_peers();
+    barrier();
+    CU(cudaStreamSynchronize(st_));
+  }
   mark(9);
   const int nf3 = (int)nf[2];
   const int dev = opts.device;
@@ -687,7 +781,87 @@ void SlabPlan<T>::setpts(int64_t M_, const T *x, const T *y, const T *z, int rou
     }
   }
   eng_->setpts(Ml, xl, yl, zl, 0, nullptr, nullptr, nullptr);
+  if (world > 1) setup_peers();
   mark(10);
+}
+
+// ------------------------------------------------------------------ peer memory (CUDA IPC)
+template<class T> void SlabPlan<T>::close_peers() {
+  for (void *q : opened_) cudaIpcCloseMemHandle(q);
+  opened_.clear();
+  for (int r = 0; r < kMaxWorld; ++r) peer_win_[r] = peer_pencil_[r] = peer_clocal_[r] = nullptr;
+  cudaGetLastError();
+  p2p_ = false;
+}
+
+// Every rank publishes the IPC handles of its window, pencil and routed-strength buffers and maps
+// the others'.  Collective (called from setpts).  Any failure on any rank (threads of one process,
+// no peer access, B200_NUFFT_SLAB_P2P=0) leaves the NCCL send/recv path in charge on all ranks.
+template<class T> void SlabPlan<T>::setup_peers() {
+  struct Pub {
+    cudaIpcMemHandle_t h[3];
+    uint32_t have[3];
+    uint32_t ok;
+  };
+  NcclApi &api    = nccl();
+  ncclComm_t comm = (ncclComm_t)comm_;
+  close_peers();
+  bar_.alloc(1);
+  const char *env = getenv("B200_NUFFT_SLAB_P2P");
+  Pub mine{};
+  mine.ok = (env && atoi(env) == 0) ? 0u : 1u;
+  void *bufs[3] = {win_.p, pencil_.p, (mode == 0 && !routed_) ? (void *)clocal_.p : nullptr};
+  for (int k = 0; k < 3; ++k) {
+    mine.have[k] = bufs[k] != nullptr;
+    if (bufs[k] && mine.ok && cudaIpcGetMemHandle(&mine.h[k], bufs[k]) != cudaSuccess) {
+      cudaGetLastError();
+      mine.ok = 0;
+    }
+  }
+  Scratch<Pub> dsend(1, st_, opts.device), dall(world, st_, opts.device);
+  std::vector<Pub> all(world);
+  CU(cudaMemcpyAsync(dsend.p, &mine, sizeof(Pub), cudaMemcpyHostToDevice, st_));
+  NC(api.AllGather(dsend.p, dall.p, sizeof(Pub), ncclChar, comm, st_));
+  CU(cudaMemcpyAsync(all.data(), dall.p, sizeof(Pub) * world, cudaMemcpyDeviceToHost, st_));
+  CU(cudaStreamSynchronize(st_));
+  uint32_t ok = 1;
+  for (int r = 0; r < world; ++r) ok &= all[r].ok;
+  if (ok) {
+    C **tab[3] = {peer_win_, peer_pencil_, peer_clocal_};
+    for (int r = 0; r < world && ok; ++r)
+      for (int k = 0; k < 3 && ok; ++k) {
+        if (r == rank) {
+          tab[k][r] = static_cast<C *>(bufs[k]);
+          continue;
+        }
+        if (!all[r].have[k]) continue;
+        void *q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[r].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok = 0;
+          break;
+        }
+        opened_.push_back(q);
+        tab[k][r] = static_cast<C *>(q);
+      }
+  }
+  // every rank must take the same path: agree on the outcome of the mapping
+  Scratch<uint32_t> flag(1, st_, opts.device);
+  CU(cudaMemcpyAsync(flag.p, &ok, sizeof(uint32_t), cudaMemcpyHostToDevice, st_));
+  NC(api.AllReduce(flag.p, flag.p, 1, ncclUint32, ncclMin, comm, st_));
+  CU(cudaMemcpyAsync(&ok, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
+  CU(cudaStreamSynchronize(st_));
+  if (!ok) {
+    close_peers();
+    return;
+  }
+  p2p_ = true;
+}
+
+// all ranks' streams meet here: work queued before it on any rank is complete on every rank's
+// side before work queued after it starts (one-word all-reduce on the plan's stream)
+template<class T> void SlabPlan<T>::barrier() {
+  NC(nccl().AllReduce(bar_.p, bar_.p, 1, ncclUint32, ncclSum, (ncclComm_t)comm_, st_));
 }
 
 // ------------------------------------------------------------------ exchanges
@@ -700,6 +874,29 @@ template<class T> void SlabPlan<T>::exchange_ghosts(bool add) {
   const int nxt = (rank + 1) % world, prv = (rank + world - 1) % world;
   const size_t plane = (size_t)nf[0] * nf[1];
   C *w = win_.p;
+  if (p2p_) {
+    // windows of the neighbours: [below ghost | their nz owned planes | above ghost]
+    const int nz_prv = zstart_[prv + 1] - zstart_[prv];
+    barrier();  // every rank has finished writing what its neighbours are about to read
+    if (add) {
+      // my first `above` planes += prev's above-ghost planes, my last `below` += next's below-ghost
+      const int64_t na = (int64_t)above * plane * 2, nb = (int64_t)below * plane * 2;
+      k_add<T><<<blocks_for(na / 4, 256), 256, 0, st_>>>(
+          reinterpret_cast<T *>(ownp_),
+          reinterpret_cast<const T *>(peer_win_[prv] + (size_t)(below + nz_prv) * plane), na);
+      k_add<T><<<blocks_for(nb / 4, 256), 256, 0, st_>>>(
+          reinterpret_cast<T *>(ownp_ + (size_t)(nz - below) * plane),
+          reinterpret_cast<const T *>(peer_win_[nxt]), nb);
+      launches += 2;
+    } else {
+      // my below ghost = prev's last `below` owned planes, my above ghost = next's first `above`
+      CU(cudaMemcpyAsync(w, peer_win_[prv] + (size_t)nz_prv * plane, below * plane * sizeof(C),
+                         cudaMemcpyDefault, st_));
+      CU(cudaMemcpyAsync(w + (size_t)(below + nz) * plane, peer_win_[nxt] + (size_t)below * plane,
+                         above * plane * sizeof(C), cudaMemcpyDefault, st_));
+    }
+    return;
+  }
   NC(api.GroupStart());
   if (add) {
     NC(api.Send(w + (size_t)(below + nz) * plane, above * plane * sizeof(C), ncclChar, nxt, comm, st_));
@@ -783,6 +980,23 @@ template<class T> void SlabPlan<T>::route_values(bool to_owner, C *user) {
   NcclApi &api    = nccl();
   ncclComm_t comm = (ncclComm_t)comm_;
   const uint32_t m = (uint32_t)M;
+  if (p2p_) {
+    RouteTable t{};
+    t.world = world;
+    for (int d = 0; d <= world; ++d) t.sendoff[d] = (uint32_t)sendoff_[d];
+    for (int d = 0; d < world; ++d) t.peer_off[d] = (uint32_t)peer_off_[d];
+    PeerPtrs<C> own{};
+    for (int r = 0; r < world; ++r) own.p[r] = peer_clocal_[r];
+    if (to_owner) {
+      if (m) k_route_peer<C, true><<<blocks_for(m, 256), 256, 0, st_>>>(user, order_.p, own, t, m);
+      barrier();  // the owners' arrays are complete
+    } else {
+      barrier();  // every owner has interpolated
+      if (m) k_route_peer<C, false><<<blocks_for(m, 256), 256, 0, st_>>>(user, order_.p, own, t, m);
+    }
+    if (m) ++launches;
+    return;
+  }
   if (to_owner && m) {
     k_gather_by<C><<<blocks_for(m, 256), 256, 0, st_>>>(user, order_.p, croute_.p, m);
     ++launches;
@@ -826,6 +1040,12 @@ template<class T> void SlabPlan<T>::execute(C *c, C *fk_block) {
   auto rows = [](int64_t n) { return (unsigned)std::max<int64_t>(1, (n + kRows - 1) / kRows); };
   C *cl = routing ? clocal_.p : c;
 
+  PeerPtrs<C> pen{};
+  for (int r = 0; r < world; ++r) pen.p[r] = peer_pencil_[r];
+  // replicated-window mode has no ghost barrier: its reduce / broadcast do not order every pair
+  // of ranks, so the peers' reads of the previous execute are fenced explicitly
+  if (p2p_ && mode == 1) barrier();
+
   if (type == 1) {
     mark(0);
     if (routing) route_values(true, c);
@@ -839,10 +1059,18 @@ template<class T> void SlabPlan<T>::execute(C *c, C *fk_block) {
     mark(3);
     fft_exec(fft2_, ownp_, sign);
     mark(4);
-    k_slab_pack<C><<<rows((int64_t)nz * ms[1]), kThreads, 0, st_>>>(ownp_, send_.p, g);
-    ++launches;
-    mark(5);
-    transpose(true);
+    if (p2p_) {  // crop + transpose in one kernel: rows stored into the owners' pencils over NVLink
+      if (mode == 1) barrier();  // the owners have finished with their pencils (see above)
+      k_slab_pack_peer<C><<<rows((int64_t)nz * ms[1]), kThreads, 0, st_>>>(ownp_, pen, g, z0);
+      ++launches;
+      mark(5);
+      barrier();  // every pencil is complete
+    } else {
+      k_slab_pack<C><<<rows((int64_t)nz * ms[1]), kThreads, 0, st_>>>(ownp_, send_.p, g);
+      ++launches;
+      mark(5);
+      transpose(true);
+    }
     mark(6);
     if (have1_) fft_exec(fft1_, pencil_.p, sign);
     mark(7);
@@ -860,9 +1088,15 @@ template<class T> void SlabPlan<T>::execute(C *c, C *fk_block) {
     mark(1);
     if (have1_) fft_exec(fft1_, pencil_.p, sign);
     mark(2);
-    transpose(false);
-    mark(3);
-    k_slab_unpack<C, T><<<rows((int64_t)nz * nf[1]), kThreads, 0, st_>>>(send_.p, ownp_, g);
+    if (p2p_) {  // transpose + zero-pad in one kernel: rows loaded from the owners' pencils
+      barrier();   // every pencil is ready (and nobody still reads this rank's planes)
+      mark(3);
+      k_slab_unpack_peer<C, T><<<rows((int64_t)nz * nf[1]), kThreads, 0, st_>>>(pen, ownp_, g, z0);
+    } else {
+      transpose(false);
+      mark(3);
+      k_slab_unpack<C, T><<<rows((int64_t)nz * nf[1]), kThreads, 0, st_>>>(send_.p, ownp_, g);
+    }
     ++launches;
     mark(4);
     fft_exec(fft2_, ownp_, sign);

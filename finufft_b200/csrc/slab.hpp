@@ -17,6 +17,13 @@
 //            => this rank's block fk[:, ylo:yhi, :] of the mode array
 //   type 2   the mirror image, ending with interpolation from the window.
 //
+// Between processes on one NVLink box the exchanges do not go through NCCL at all: every rank maps
+// the other ranks' window, pencil and strength buffers (CUDA IPC) and the kernels read / write
+// them directly - the ghost planes are ADDED straight from the neighbours' windows, the pack
+// kernel STORES the cropped modes into the destination ranks' pencils, the routing kernel stores
+// the strengths into the owners' arrays - with three stream barriers per execute (a one-word
+// ncclAllReduce each) in place of the send/recv pairs.
+//
 // Points: `routed = 1` promises that every point already folds into the rank's slab.  Otherwise
 // setpts routes them: plane histogram -> all-reduce -> each point goes to the rank that owns its
 // plane (all-to-all of coordinates once, of the strengths / values at every execute; both are
@@ -91,6 +98,13 @@ template<class T> class SlabPlan {
   void transpose(bool to_pencil);
   void route_points(const T *x, const T *y, const T *z);
   void route_values(bool to_owner, C *user);
+  // peer-memory path (ranks in separate processes on one NVLink / NVSwitch box): the window,
+  // the pencils and the routed strengths of every rank are mapped into every other rank with
+  // CUDA IPC, and the exchanges ride inside the kernels as loads / stores over NVLink, ordered
+  // by stream barriers (slab.cu).  Falls back to NCCL send/recv when the mapping fails.
+  void setup_peers();
+  void close_peers();
+  void barrier();
   void mark(int i);
   int owner_of_plane(int p) const;
 
@@ -106,6 +120,11 @@ template<class T> class SlabPlan {
   std::vector<Seg> segs_;
   std::vector<uint64_t> sendcnt_, recvcnt_, sendoff_, recvoff_;  // points, routing
   bool routed_ = true;
+  bool p2p_    = false;
+  C *peer_win_[16] = {}, *peer_pencil_[16] = {}, *peer_clocal_[16] = {};
+  std::vector<void *> opened_;
+  std::vector<uint64_t> peer_off_;  // where this rank's routed block starts in rank d's clocal_
+  DevBuf<uint32_t> bar_;
   cufftHandle fft2_ = 0, fft1_ = 0;
   bool have2_ = false, have1_ = false;
   cudaEvent_t ev_[12] = {};

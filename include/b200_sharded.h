@@ -18,6 +18,12 @@
  *            being an even split of ms2 over the ranks (b200_slab_info).  b200_slab_gather_modes
  *            assembles the full ms3 x ms2 x ms1 array on every rank, b200_slab_slice_modes cuts
  *            a rank's block out of a full array.
+ * Exchanges: when the ranks are separate processes with peer access (one NVLink / NVSwitch box),
+ * every rank maps the others' buffers with CUDA IPC and the kernels load / store peer memory
+ * directly (ghost planes added from the neighbours' windows, cropped modes stored into the
+ * owners' pencils, strengths stored into the owners' arrays), ordered by one-word all-reduces;
+ * otherwise grouped ncclSend/ncclRecv.  B200_NUFFT_SLAB_P2P=0 forces the NCCL path.
+ * makeplan, setpts, execute, gather_modes and destroy are collective over the ranks.
  * ntransf = 1.  Batched transforms shard by vectors instead (no communication): give each rank
  * an ordinary plan for its slice of the vectors.
  */
