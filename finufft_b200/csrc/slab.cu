@@ -551,7 +551,7 @@ SlabPlan<T>::SlabPlan(int type_, const int64_t *nmodes, int iflag, double tol_, 
 
 template<class T> SlabPlan<T>::~SlabPlan() {
   cudaStreamSynchronize(st_);
-  if (!opened_.empty() || p2p_) {
+  if (peers_tried_) {
     // no rank may free a buffer another rank still has mapped: unmap, then meet (collective)
     close_peers();
     try {
@@ -560,6 +560,7 @@ template<class T> SlabPlan<T>::~SlabPlan() {
     }
     cudaStreamSynchronize(st_);
   }
+  for (void *q : retired_) cudaFree(q);
   eng_.reset();
   if (comm_) nccl().CommDestroy((ncclComm_t)comm_);
   if (have2_) cufftDestroy(fft2_);
@@ -574,12 +575,24 @@ template<class T> int SlabPlan<T>::owner_of_plane(int p) const {
   return r;
 }
 
+// A buffer other ranks may have mapped is never freed while mapped: when it has to grow, the old
+// allocation is parked until the next collective unmapping (setup_peers).
+template<class T> void SlabPlan<T>::grow_exported(DevBuf<C> &b, size_t count) {
+  if (count <= b.n && b.p) return;
+  if (b.p && peers_tried_) {
+    retired_.push_back(b.p);
+    b.p = nullptr;
+    b.n = 0;
+  }
+  b.alloc(count);
+}
+
 // the spread / interp engine on a window of `n` planes from global plane `org`
 template<class T> void SlabPlan<T>::make_engine(int org, int n) {
   if (n >= nf[2]) org = 0, n = (int)nf[2];
   win_org = org;
   win_n   = n;
-  win_.alloc((size_t)n * nf[0] * nf[1]);
+  grow_exported(win_, (size_t)n * nf[0] * nf[1]);
   if (eng_ && eng_org_ == org && eng_n_ == n) return;
   EngineOpts eo       = opts;
   eo.spreadinterponly = 1;
@@ -687,7 +700,7 @@ void SlabPlan<T>::route_points(const T *x, const T *y, const T *z) {
       CU(cudaMemcpyAsync(dst[a] + recvoff_[rank], src[a] + sendoff_[rank],
                          sendcnt_[rank] * sizeof(T), cudaMemcpyDeviceToDevice, st_));
   croute_.alloc(std::max<size_t>(1, M));
-  clocal_.alloc(std::max<size_t>(1, Ml));
+  grow_exported(clocal_, std::max<size_t>(1, Ml));
 }
 
 template<class T>
@@ -697,12 +710,6 @@ void SlabPlan<T>::setpts(int64_t M_, const T *x, const T *y, const T *z, int rou
   if (M_ > std::numeric_limits<int32_t>::max()) throw Failure{ERR_NDATA_NOTVALID};
   M = M_;
   NvtxRange range("b200::slab setpts (route + sort)");
-  if (!opened_.empty() || p2p_) {  // buffers may be reallocated below: unmap everywhere first
-    CU(cudaStreamSynchronize(st_));
-    close_peers();
-    barrier();
-    CU(cudaStreamSynchronize(st_));
-  }
   mark(9);
   const int nf3 = (int)nf[2];
   const int dev = opts.device;
@@ -805,12 +812,29 @@ template<class T> void SlabPlan<T>::setup_peers() {
   };
   NcclApi &api    = nccl();
   ncclComm_t comm = (ncclComm_t)comm_;
-  close_peers();
   bar_.alloc(1);
+  void *bufs[3] = {win_.p, pencil_.p, (mode == 0 && !routed_) ? (void *)clocal_.p : nullptr};
+  {  // mapping is slow (milliseconds): keep the existing one unless some rank's buffers moved
+    uint32_t changed = !peers_tried_;
+    for (int k = 0; k < 3; ++k) changed |= bufs[k] != published_[k];
+    Scratch<uint32_t> flag(1, st_, opts.device);
+    CU(cudaMemcpyAsync(flag.p, &changed, sizeof(uint32_t), cudaMemcpyHostToDevice, st_));
+    NC(api.AllReduce(flag.p, flag.p, 1, ncclUint32, ncclMax, comm, st_));
+    CU(cudaMemcpyAsync(&changed, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st_));
+    CU(cudaStreamSynchronize(st_));
+    if (!changed) return;
+  }
+  // unmap everywhere, then meet, and only then free what was replaced while mapped
+  close_peers();
+  barrier();
+  CU(cudaStreamSynchronize(st_));
+  for (void *q : retired_) cudaFree(q);
+  retired_.clear();
+  peers_tried_ = true;
+  for (int k = 0; k < 3; ++k) published_[k] = bufs[k];
   const char *env = getenv("B200_NUFFT_SLAB_P2P");
   Pub mine{};
   mine.ok = (env && atoi(env) == 0) ? 0u : 1u;
-  void *bufs[3] = {win_.p, pencil_.p, (mode == 0 && !routed_) ? (void *)clocal_.p : nullptr};
   for (int k = 0; k < 3; ++k) {
     mine.have[k] = bufs[k] != nullptr;
     if (bufs[k] && mine.ok && cudaIpcGetMemHandle(&mine.h[k], bufs[k]) != cudaSuccess) {

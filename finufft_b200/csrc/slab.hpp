@@ -122,7 +122,10 @@ template<class T> class SlabPlan {
   bool routed_ = true;
   bool p2p_    = false;
   C *peer_win_[16] = {}, *peer_pencil_[16] = {}, *peer_clocal_[16] = {};
-  std::vector<void *> opened_;
+  std::vector<void *> opened_, retired_;  // peers' mappings; own buffers replaced while mapped
+  void *published_[3] = {nullptr, nullptr, nullptr};
+  bool peers_tried_   = false;
+  void grow_exported(DevBuf<C> &b, size_t count);
   std::vector<uint64_t> peer_off_;  // where this rank's routed block starts in rank d's clocal_
   DevBuf<uint32_t> bar_;
   cufftHandle fft2_ = 0, fft1_ = 0;
