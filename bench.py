@@ -273,8 +273,16 @@ def main():
     sharded = world > 1 and dim == 3 and ntr == 1
     batched = world > 1 and ntr > 1
     if sharded:
-        sharding = (f"one transform sharded over {world} GPUs by z-slabs of the fine grid; every "
-                    "rank holds M/N arbitrary points (routed by the library), outputs sharded")
+        if args.dist == "cluster":
+            sharding = (f"one transform sharded over {world} GPUs; every rank holds M/N of the "
+                        "(clustered) points, the library replicates the occupied window of the "
+                        "grid and reduces it onto the owning slabs; outputs sharded")
+        else:
+            sharding = (f"one transform sharded over {world} GPUs by z-slabs of the fine grid; "
+                        "inputs resident in the HBM of the GPU that owns them (every rank holds "
+                        "the M/N points of its slab), both exchanges inside the step, outputs "
+                        "sharded; `arbitrary_points` = same with every rank holding an arbitrary "
+                        "M/N share that the library routes inside the step")
     elif batched:
         sharding = f"the {ntr} vectors split across {world} GPUs, no collective"
     elif world > 1:
@@ -382,15 +390,29 @@ def main():
         info = sp.info()
         nf = info["nf"]
         pts_h = perfdata.points(3, Ml, rt, args.dist, nf, first=lo)        # x, y, z share
-        x, y, z = (torch.from_numpy(p).to(dev) for p in pts_h)
-        sp.setpts(z, y, x)          # untimed: module loading, pools, NCCL channels
-        torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        sp.setpts(z, y, x)
-        torch.cuda.synchronize()
-        setpts_wall_ms = allmax((time.perf_counter() - t0) * 1e3)
-        setpts_ms = allmax(sp.stage_ms()["setpts"])
+        x, y, z_any = (torch.from_numpy(p).to(dev) for p in pts_h)
+        resident = args.dist != "cluster"
+        if resident:
+            # the same streams, the z stream mapped into this rank's slab: uniform points, every
+            # one of them owned by this rank (a margin of 1e-5 slab widths keeps the single-
+            # precision fold on the right side of the slab faces)
+            u = np.empty(Ml, dtype=rt)
+            perfdata.fill(u, "Z", 1.0, 0.0, first=lo)                     # U(-1, 1)
+            frac = (0.5 * (u.astype(np.float64) + 1.0)) * (1 - 2e-5) + 1e-5
+            zres = (-np.pi + (2 * np.pi / nf[2]) * (info["z0"] + info["nz"] * frac)).astype(rt)
+            z = torch.from_numpy(zres).to(dev)
+        else:
+            z = z_any
+
+        def set_points(zz, routed):
+            sp.setpts(zz, y, x, routed=routed)          # untimed: module loading, pools, mappings
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            sp.setpts(zz, y, x, routed=routed)
+            torch.cuda.synchronize()
+            return (allmax((time.perf_counter() - t0) * 1e3), allmax(sp.stage_ms()["setpts"]))
+        setpts_wall_ms, setpts_ms = set_points(z, resident)
         info = sp.info()
         if type_ == 1:
             h_in = [torch.from_numpy(perfdata.strengths(Ml, dtype, "C", first=lo)).pin_memory(),
@@ -446,23 +468,22 @@ def main():
                 ms_g = timed(lambda i: sp.gather_modes(sp.execute(data[i & 1], out)),
                              max(5, args.steps // 2), 2)
                 extras["with_mode_gather"] = {"ms_per_step": ms_g, "value": M / (ms_g * 1e-3)}
-            # points pre-partitioned by slab (caller-side domain decomposition): no routing
-            keep = None
-            zf = torch.addcmul(torch.full_like(z, 0.5), z, torch.full_like(z, 0.15915494309189535))
-            plane = torch.clamp(((zf - torch.floor(zf)) * nf[2]).long(), max=nf[2] - 1)
-            # rank r's share of every slab becomes "its" points: fold them into its own slab by
-            # shifting z by whole slabs (keeps the distribution, makes every point local)
-            owner = torch.clamp(plane // (nf[2] // world), max=world - 1)
-            zshift = z + (rank - owner).to(z.dtype) * (2 * np.pi / world)
-            try:
-                sp.setpts(zshift, y, x, routed=True)
-                din = data[0] if type_ == 1 else data[0]
+            # every rank holding an ARBITRARY M/N share of the points: the library routes the
+            # coordinates at setpts and the strengths / values inside every step
+            if resident:
+                wall_any, setpts_any = set_points(z_any, False)
                 ms_r = timed(lambda i: sp.execute(data[i & 1], out), max(5, args.steps // 2), 2)
-                extras["pre_partitioned_points"] = {"ms_per_step": ms_r,
-                                                   "value": M / (ms_r * 1e-3)}
-            except F.NufftError as exc:  # a point on a slab edge rounded the other way
-                extras["pre_partitioned_points"] = {"unavailable": str(exc)}
-            del zshift, owner, plane, zf, keep
+                st_any = {}
+                for i in range(3):
+                    barrier()
+                    sp.execute(data[i & 1], out)
+                    for k, v in sp.stage_ms().items():
+                        st_any.setdefault(k, []).append(v)
+                extras["arbitrary_points"] = {
+                    "ms_per_step": ms_r, "value": M / (ms_r * 1e-3), "unit": "points/s",
+                    "route_values_ms": allmax(float(np.mean(st_any["route_values"]))),
+                    "setpts_ms": setpts_any,
+                    "note": "strengths / values routed between the GPUs inside the timed step"}
         win_cells = info["win_n"] * nf[0] * nf[1]
         abytes = algorithmic_bytes(3, info["M_local"], win_cells, rbytes)
         kernel_ms = stage_avg["spreadinterp"]
@@ -507,7 +528,9 @@ def main():
                     "value_with_setpts": M / ((ms_per_step + setpts_ms) * 1e-3),
                     "accuracy": acc,
                     "plan": {"ns": info["ns"], "nf": nf, "mode": info["mode"],
-                             "window_planes": info["win_n"], "M_local_rank0": info["M_local"]}}
+                             "window_planes": info["win_n"], "M_local_rank0": info["M_local"],
+                             "points": "resident on the owning GPU" if resident else
+                                       "arbitrary share per rank (replicated-window mode)"}}
             line.update(extras)
             if replicas:
                 line["replicas"] = replicas

@@ -18,7 +18,7 @@ G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 for f in glob.glob(os.path.join(G, f"{tag}_bench_*.json")) + glob.glob(os.path.join(G, f"{tag}_bench_*.txt")):
     shutil.copy(f, P)
-for f in (f"{tag}_pytest_gpu.log", f"{tag}_launches_c3_t1.csv", f"{tag}_launches_setpts.csv",
+for f in (f"{tag}_pytest_gpu.log", f"{tag}_launches_c3_t1.csv", f"{tag}_launches_setpts.csv", f"{tag}_launches_slab.csv",
           f"{tag}_smi.txt"):
     if os.path.exists(os.path.join(G, f)):
         shutil.copy(os.path.join(G, f), P)

@@ -41,4 +41,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sw
 # setpts kernels: one full capture each (first launch of k_part = raw pass, second = record pass)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_part|k_seg_sort|k_bin_hist" -c 4 -f \
   -o $out/${tag}_setpts python tools/prof_run.py --workload c3_t1 --reps 1 > $out/${tag}_ncu_full_setpts.log 2>&1
+# the sharded plan at world = 1: launch list of the slab kernels
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 120 --csv \
+  --log-file $out/${tag}_launches_slab.csv python tools/prof_run_sharded.py > $out/${tag}_ncu_slab.log 2>&1
+tail -3 $out/${tag}_ncu_slab.log
 ls -la $out | tail -40
