@@ -95,7 +95,8 @@ INTROSPECT = ["b200_get_plan_info", "b200_get_sort_permutation", "b200_get_raw_s
               "b200_get_sort_path", "b200_get_window_table",
               "b200_get_phihat", "b200_enable_profiling", "b200_get_stage_ms",
               "b200_get_launch_count", "b200_host_kernel", "b200_host_fine_grid",
-              "b200_host_fseries", "b200_version"]
+              "b200_host_fseries", "b200_host_smallest_sigma", "b200_host_sigma_feasible",
+              "b200_host_choose_sigma", "b200_version"]
 SHARDED = ["b200_slab_unique_id", "b200_slab_get_info", "b200_slab_get_stage_ms",
            "b200_slab_get_launch_count"] + [
     f"b200_slab{p}_{n}" for p in ("", "f")
@@ -170,6 +171,12 @@ def load():
     lib.b200_host_kernel.restype = ci
     lib.b200_host_fine_grid.argtypes = [dbl, i64, ci]
     lib.b200_host_fine_grid.restype = i64
+    lib.b200_host_smallest_sigma.argtypes = [dbl, ci, ci, ci, dbl]
+    lib.b200_host_smallest_sigma.restype = dbl
+    lib.b200_host_sigma_feasible.argtypes = [dbl, dbl, ci, ci, ci, dbl]
+    lib.b200_host_sigma_feasible.restype = ci
+    lib.b200_host_choose_sigma.argtypes = [dbl, ci, ci, ci, C.POINTER(i64), dbl]
+    lib.b200_host_choose_sigma.restype = dbl
     lib.b200_host_fseries.argtypes = [i64, ci, ci, ci, vp, vp]
     lib.b200_host_fseries.restype = ci
     lib.b200_version.restype = C.c_char_p

@@ -154,6 +154,7 @@ EngineOpts from_host_opts(const finufft_opts *o) {
   e.debug   = d.debug;
   e.allow_eps_too_small = d.allow_eps_too_small;
   e.check_sigma         = 1;
+  e.auto_sigma          = d.upsampfac == 0.0;  // include/finufft_opts.h:44: 0 = auto
   // include/finufft_opts.h:41: 0 don't sort, 1 sort, 2 heuristic choice.  The reference's
   // heuristic (spreadinterp.hpp:161-163) skips the sort for 1D type 2 / tiny grids because a
   // CPU thread streams such points well; on this device sorted points always win, so the
@@ -837,6 +838,17 @@ int b200_host_kernel(double tol, int dim, int type, double sigma, int is_float, 
       std::memcpy(coef, c.data(), c.size() * sizeof(double));
     }
   });
+}
+double b200_host_smallest_sigma(double tol, int dim, int type, int is_float, double maxN) {
+  return smallest_feasible_sigma(tol, dim, type, is_float != 0, maxN);
+}
+int b200_host_sigma_feasible(double sigma, double tol, int dim, int type, int is_float,
+                             double maxN) {
+  return sigma_feasible(sigma, tol, dim, type, is_float != 0, maxN) ? 1 : 0;
+}
+double b200_host_choose_sigma(double tol, int dim, int type, int is_float, const int64_t *modes,
+                              double npoints) {
+  return choose_sigma(tol, dim, type, is_float != 0, modes, npoints);
 }
 int64_t b200_host_fine_grid(double sigma, int64_t modes, int ns) {
   return fine_grid_size(sigma, modes, ns);

@@ -128,8 +128,9 @@ Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr
   DeviceGuard guard(opts.device);
   scratch_pool_retain(opts.device);  // setpts scratch: the library's own pool (scratch.hpp)
   pool_held_ = true;
-  tol   = tol_;
+  tol = tol_req_ = tol_;
   sigma = opts.upsampfac == 0.0 ? 2.0 : opts.upsampfac;
+  if (opts.upsampfac != 0.0 || type == 3 || opts.spreadinterponly) opts.auto_sigma = 0;
   batch = opts.maxbatch > 0 ? std::min(opts.maxbatch, ntr) : std::min(ntr, 8);
   if (opts.maxsub < 32) opts.maxsub = 32;
   if (const char *env = getenv("B200_NUFFT_SWEEP")) opts.sweep = atoi(env);  // debugging aids
@@ -573,6 +574,20 @@ void Engine<T>::setpts(int64_t M_, const T *x, const T *y, const T *z, int64_t N
     return;
   }
   M = M_;
+  if (opts.auto_sigma) {
+    // the reference CPU library picks sigma here from the number of points
+    // (include/finufft/setpts.hpp:107-161); same candidates, this device's cost model
+    const double s_new = choose_sigma(tol_req_, dim, type, std::is_same<T, float>::value, ms,
+                                      (double)M);
+    if (std::abs(s_new - sigma) > 1e-12) {
+      CU(cudaStreamSynchronize(opts.stream));
+      sigma = s_new;
+      tol   = tol_req_;
+      plan_kernel();
+      plan_grid();
+      coef_dev_.release();
+    }
+  }
   if (opts.check_sigma) {  // include/finufft/setpts.hpp:29-53
     const double eps  = std::numeric_limits<T>::epsilon();
     const double glen = (double)*std::max_element(nf, nf + dim);

@@ -43,6 +43,7 @@ struct EngineOpts {
   int sweep            = 1;     // 3D float: tube-sweep kernels (0 = generic kernels)
   int stage            = -1;    // two-level strength permutation (stage.cuh): -1 auto, 0 off, 1 on
   int check_sigma      = 0;     // host (finufft_*) entry points apply the CPU feasibility rule
+  int auto_sigma       = 0;     // upsampfac = 0 on the host API: choose sigma at setpts (types 1, 2)
   int partition        = 1;     // setpts: 1 partition sort where it pays, 2 always, 0 counting sort
   // bin sort at setpts: 1 sort, 0 keep the user's order and run the point-driven kernels
   // (direct.cuh), 2 = library's choice (this engine: sort).  gpu_sort / spread_sort of the
@@ -180,6 +181,7 @@ template<class T> class Engine {
   bool radix_order_ = false;  // sidx_ is the reference permutation as it stands
   bool part_used_   = false;  // the last setpts took the partition sort (partition.cuh)
   bool pool_held_   = false;
+  double tol_req_   = 0;      // the caller's tolerance (tol is what the kernel choice clamped it to)
   bool unsorted_    = false;  // the last setpts kept the user's order (opts.sort = 0)
   DevBuf<T> coef_dev_;        // polynomial table for the point-driven kernels
   // type 3

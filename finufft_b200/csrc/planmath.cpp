@@ -318,6 +318,100 @@ double least_sigma(double tol, int dim, int ns, double eps_mach, double gridlen)
   return std::min(pure + std::max(corr, 0.0), 2.0);
 }
 
+bool sigma_feasible(double sigma, double tol, int dim, int type, bool is_float, double maxN) {
+  if (!(sigma > 1.0)) return false;
+  const double eps = is_float ? (double)std::numeric_limits<float>::epsilon()
+                              : std::numeric_limits<double>::epsilon();
+  const int cap    = is_float ? kMaxNsF32 : kMaxNsF64;
+  // width the aliasing law asks for (no clamping) against the width the plan would use
+  const double rate = kPi * std::sqrt(1.0 - 1.0 / sigma);
+  const int ideal   = (int)std::ceil(std::log(aliasing_prefactor(dim, type) / tol) / rate + 1.0);
+  int w = std::min(std::max(ideal, 2), cap);
+  if (is_float && sigma < 1.4) w = std::min(w, 8);
+  if (w < ideal) return false;
+  if (type == 3) return true;
+  const int64_t nf = fine_grid_size(sigma, (int64_t)maxN, w);
+  if (nf < 0) return false;
+  return least_sigma(tol, dim, w, eps, (double)nf) <= sigma;
+}
+
+double smallest_feasible_sigma(double tol, int dim, int type, bool is_float, double maxN) {
+  constexpr double lo0 = 1.15, hi0 = 2.5;
+  if (sigma_feasible(lo0, tol, dim, type, is_float, maxN)) return lo0;
+  if (!sigma_feasible(hi0, tol, dim, type, is_float, maxN)) return hi0;
+  double lo = lo0, hi = hi0;
+  for (int i = 0; i < 40; ++i) {
+    const double mid = 0.5 * (lo + hi);
+    (sigma_feasible(mid, tol, dim, type, is_float, maxN) ? hi : lo) = mid;
+  }
+  return hi;
+}
+
+namespace {
+int width_at(double tol, int dim, int type, double sigma, bool is_float) {
+  int ns = 0;
+  double beta = 0, tu = 0;
+  if (choose_kernel(tol, dim, type, sigma, is_float, true, ns, beta, tu)) return 16;
+  return ns;
+}
+// milliseconds of one execute on a B200 (measured: profiles/r2g_bench_*.json)
+double cost_ms(int dim, bool is_float, const int64_t *modes, double sigma, int ns, double M) {
+  double cells = 1.0, stencil = 1.0;
+  for (int d = 0; d < dim; ++d) {
+    cells *= (double)fine_grid_size(sigma, modes[d], ns);
+    stencil *= ns;
+  }
+  double base, per_cell;  // ms per point: base + per_cell * ns^dim
+  if (dim == 3) {
+    const bool sweep = is_float && ns <= 7;            // k_sweep3: 8.05 ms per 1e8 points at ns = 7
+    base = 1.0e-8, per_cell = sweep ? 2.1e-10 : 9.5e-10;  // generic kernels: 35 ms at ns = 7
+    if (!is_float) per_cell *= 2.0;
+  } else if (dim == 2) {
+    base = is_float ? 1.2e-8 : 2.0e-8;                  // k_sweep2: 2.42 ms (f32, ns 6), 8.1 ms per 1e8 (f64, ns 10)
+    per_cell = is_float ? 3.4e-10 : 6.1e-10;
+  } else {
+    base = 2.0e-8, per_cell = is_float ? 1.4e-9 : 2.7e-9;  // generic 1D: 4.7 ms per 1e8 (f64, ns 10)
+  }
+  const double spread = M * (base + per_cell * stencil);
+  // cuFFT + the zero / deconvolve passes over the grid: 1.08 + 0.27 ms on 512^3 (f32)
+  const double fft = cells * std::log2(std::max(cells, 2.0)) * 3.0e-10 * (is_float ? 1.0 : 2.0) +
+                     cells * 2.0e-9 * (is_float ? 1.0 : 2.0);
+  return spread + fft;
+}
+}  // namespace
+
+double choose_sigma(double tol, int dim, int type, bool is_float, const int64_t *modes,
+                    double npoints) {
+  const double eps = is_float ? (double)std::numeric_limits<float>::epsilon()
+                              : std::numeric_limits<double>::epsilon();
+  double t = is_float ? (double)(float)tol : tol;
+  if (t < eps) t = eps;
+  double maxN = 1.0;
+  for (int d = 0; d < dim; ++d) maxN = std::max(maxN, (double)modes[d]);
+  const double smin = smallest_feasible_sigma(t, dim, type, is_float, maxN);
+  if (!sigma_feasible(smin, t, dim, type, is_float, maxN)) return 2.0;  // tol out of reach: default
+  double best = smin;
+  double best_cost = cost_ms(dim, is_float, modes, smin, width_at(t, dim, type, smin, is_float), npoints);
+  // candidates stop at sigma = 2 (the reference searches up to 2.5; above 2 the fine grid grows
+  // faster than the kernel narrows on this device, and 2 is where every kernel family is tuned)
+  constexpr double smax = 2.0;
+  if (smin >= smax) return smax;
+  const int ns_lo = width_at(t, dim, type, smax, is_float);
+  for (int w = width_at(t, dim, type, smin, is_float) - 1; w >= ns_lo; --w) {
+    const double s = std::min(std::max(sigma_reaching(t, dim, type, w), smin), smax);
+    if (!sigma_feasible(s, t, dim, type, is_float, maxN)) continue;
+    const double c = cost_ms(dim, is_float, modes, s, width_at(t, dim, type, s, is_float), npoints);
+    if (c < best_cost) best = s, best_cost = c;
+  }
+  // sigma = 2 is the value every kernel family is tuned and tested at: prefer it unless another
+  // candidate is clearly (> 10 %) cheaper
+  if (sigma_feasible(2.0, t, dim, type, is_float, maxN)) {
+    const double c2 = cost_ms(dim, is_float, modes, 2.0, width_at(t, dim, type, 2.0, is_float), npoints);
+    if (c2 <= 1.1 * best_cost) return 2.0;
+  }
+  return best;
+}
+
 // ------------------------------------------------------------------ type 3
 void type3_grid(double sigma, double X, double S, int ns, int64_t &nf, double &h, double &gam) {
   double Xs = X, Ss = S;  // enforce X*S >= 1, also when either is zero

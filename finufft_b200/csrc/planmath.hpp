@@ -71,6 +71,21 @@ template<class T> double eval_table(double x, int ns, int nc, const T *coef);
 // Least sigma that can reach tol on a grid of this length (check_sigma rule).
 double least_sigma(double tol, int dim, int ns, double eps_mach, double gridlen);
 
+// Would the plan pipeline accept this sigma at this tolerance (kernel width not clamped, and for
+// types 1/2 the rounding-floor rule on the fine grid sigma would build)?  maxN = largest mode
+// count over the dimensions.  Reference src/common/kernel.cpp:203-228 (upsampfac_feasible).
+bool sigma_feasible(double sigma, double tol, int dim, int type, bool is_float, double maxN);
+// Smallest accepted sigma in [1.15, 2.5] (bisection), 2.5 if none.  Reference
+// src/common/kernel.cpp:231-257 (analytic_upsampfac).
+double smallest_feasible_sigma(double tol, int dim, int type, bool is_float, double maxN);
+// Automatic upsampfac for a type-1/2 plan on this device: the candidate set of the reference's
+// heuristic (include/finufft/heuristics.hpp:82-128: the smallest feasible sigma, then for every
+// narrower kernel width the smallest sigma that reaches it, up to 2.5), scored with a B200 cost
+// model (spread / interp time per point by dimension, width, precision and kernel family + FFT
+// and grid-pass time per fine-grid cell; constants from profiles/r2g_bench_*.json).
+double choose_sigma(double tol, int dim, int type, bool is_float, const int64_t *modes,
+                    double npoints);
+
 // Type-3 fine grid (nf, spacing h, rescale gam) for half-widths X (space) and S (frequency).
 void type3_grid(double sigma, double X, double S, int ns, int64_t &nf, double &h, double &gam);
 

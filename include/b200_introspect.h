@@ -44,6 +44,13 @@ int b200_get_launch_count(void *plan, uint64_t *count);
 int b200_host_kernel(double tol, int dim, int type, double sigma, int is_float, int allow_small,
                      int *ns, double *beta, int *nc, void *coef);
 int64_t b200_host_fine_grid(double sigma, int64_t modes, int ns);
+/* automatic upsampfac (host API, upsampfac = 0): smallest sigma the plan pipeline accepts
+ * (reference src/common/kernel.cpp:231-257), the feasibility test itself (:203-228), and the
+ * value setpts picks for npoints points on this device's cost model */
+double b200_host_smallest_sigma(double tol, int dim, int type, int is_float, double maxN);
+int b200_host_sigma_feasible(double sigma, double tol, int dim, int type, int is_float, double maxN);
+double b200_host_choose_sigma(double tol, int dim, int type, int is_float, const int64_t *modes,
+                              double npoints);
 int b200_host_fseries(int64_t nf, int ns, int nc, int is_float, const void *coef, void *out);
 /* library build tag, e.g. "finufft_b200 0.1 sm_100a" */
 const char *b200_version(void);

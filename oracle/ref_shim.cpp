@@ -86,6 +86,18 @@ double ref_lowest_sigma(double tol, int dim, int ns, double eps_mach, double gri
   return finufft::common::lowest_sigma(tol, dim, ns, eps_mach, gridlen);
 }
 
+// the reference's own sigma search (src/common/kernel.cpp:203-257)
+double ref_analytic_upsampfac(double tol, int dim, int type, int is_float, double maxN) {
+  return finufft::common::analytic_upsampfac(tol, dim, type, is_float ? 1.1920929e-07 : 2.220446049250313e-16,
+                                             is_float ? 12 : 16, is_float != 0, maxN);
+}
+int ref_upsampfac_feasible(double sigma, double tol, int dim, int type, int is_float, double maxN) {
+  return finufft::common::upsampfac_feasible(sigma, tol, dim, type,
+                                             is_float ? 1.1920929e-07 : 2.220446049250313e-16,
+                                             is_float ? 12 : 16, is_float != 0, maxN)
+             ? 1 : 0;
+}
+
 void ref_nhg_type3(double sigma, double X, double S, int ns, int64_t *nf, double *h,
                    double *gam) {
   auto [a, b, c] = finufft::common::nhg_type3(sigma, X, S, ns, (int64_t)1e12);

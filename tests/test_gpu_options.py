@@ -158,3 +158,37 @@ def test_oneshot_finufftf3d3_and_1d1(cuda, oracle):
     op = _checker(oracle)(1, [ms], 1, 1, tol, np.float64, nthr=4)
     op.setpts(x)
     assert oracle.relerr(fk, op.execute(c)) <= 2 * tol
+
+
+@pytest.mark.parametrize("prec,tol,dim,modes,M", [
+    ("d", 1e-9, 2, (512, 512), 2_000),          # sparse: the FFT dominates, sigma drops to ~1.2
+    ("f", 1e-4, 3, (96, 96, 96), 500),
+    ("d", 1e-6, 1, (20_000,), 300),
+    ("d", 1e-9, 2, (64, 64), 200_000),          # dense: sigma stays 2
+])
+def test_auto_upsampfac_host_api(cuda, oracle, prec, tol, dim, modes, M):
+    """finufft_opts.upsampfac = 0 on the host API: sigma is chosen at setpts (reference
+    include/finufft/setpts.hpp:107-161, heuristics.hpp:82-128) from the number of points; the plan
+    is rebuilt for it and the result matches the reference library run at that same sigma."""
+    import finufft_b200 as F
+    rt, ct = (np.float32, np.complex64) if prec == "f" else (np.float64, np.complex128)
+    rng = np.random.default_rng(33)
+    pts = make_points(rng, dim, M, rt)[:dim]
+    for type_ in (1, 2):
+        hp = F.HostPlan(type_, modes, 1, tol, 1, ct, allow_eps_too_small=1)   # upsampfac = 0
+        assert hp.info()["sigma"] == 2.0                                       # until setpts
+        hp.setpts(*pts)
+        sigma = hp.info()["sigma"]
+        if M < 10_000:
+            assert 1.15 <= sigma < 2.0, sigma
+        else:
+            assert sigma == 2.0
+        data = _rand_c(rng, (M,) if type_ == 1 else modes, ct)
+        got = hp.execute(data)
+        op = _checker(oracle)(type_, list(modes[::-1]), 1, 1, tol, rt, sigma=sigma, nthr=4)
+        op.setpts(*(pts[::-1] + [None] * (3 - dim)))
+        assert op.ns == hp.info()["ns"] and op.nf == hp.info()["nf"]
+        assert oracle.relerr(got, op.execute(data)) <= 2 * tol, (type_, sigma)
+        # a second, dense point set on the same plan: sigma is chosen again
+        hp.destroy()
+        op.destroy()

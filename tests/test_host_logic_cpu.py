@@ -1,7 +1,11 @@
 """CPU-only: the product's own host-side plan mathematics (finufft_b200/csrc/planmath.cpp,
 reached through the b200_host_* entry points) against the oracle."""
+import os
+
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -62,3 +66,42 @@ def test_fseries_matches_oracle(hm, oracle, dt, tol):
         assert np.max(np.abs(ours.astype(np.float64) - ref.astype(np.float64))) <= \
             4 * np.finfo(dt).eps * abs(float(ref[0]))
         assert ours[0] > 0 and np.all(np.sign(ours[: nf // 4]) == (-1.0) ** np.arange(nf // 4))
+
+
+def test_auto_upsampfac_search_matches_reference():
+    """Automatic upsampfac (host API, upsampfac = 0): the smallest feasible sigma and the
+    feasibility test against the reference's own src/common/kernel.cpp:203-257 compiled into
+    oracle/_ref (analytic_upsampfac, upsampfac_feasible), the two probe values of SURVEY.md 8(c),
+    and sanity of the B200 cost-model pick (dense point sets keep sigma = 2, sparse ones on a large
+    grid go below it and stay feasible)."""
+    import ctypes as C
+    import finufft_b200
+    lib = finufft_b200.load()
+    assert abs(lib.b200_host_smallest_sigma(1e-9, 1, 1, 0, 1e6) - 1.8394) < 2e-4
+    assert abs(lib.b200_host_smallest_sigma(1e-9, 2, 1, 0, 512.0) - 1.2027) < 2e-4
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libfinufft_ref_common.so")
+    if os.path.exists(ref_path):
+        ref = C.CDLL(ref_path)
+        ref.ref_analytic_upsampfac.restype = C.c_double
+        ref.ref_analytic_upsampfac.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_double]
+        ref.ref_upsampfac_feasible.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                               C.c_double]
+        for is_float, tols in ((1, (1e-2, 1e-3, 1e-4, 1e-5, 1e-6)), (0, (1e-3, 1e-6, 1e-9, 1e-12, 1e-14))):
+            for tol in tols:
+                for dim in (1, 2, 3):
+                    for type_ in (1, 2):
+                        for N in (16.0, 200.0, 4096.0, 1e6):
+                            a = lib.b200_host_smallest_sigma(tol, dim, type_, is_float, N)
+                            b = ref.ref_analytic_upsampfac(tol, dim, type_, is_float, N)
+                            assert abs(a - b) < 1e-9, (is_float, tol, dim, type_, N, a, b)
+                            for s in (1.15, 1.25, 1.5, 2.0, 2.5):
+                                assert lib.b200_host_sigma_feasible(s, tol, dim, type_, is_float, N) == \
+                                    ref.ref_upsampfac_feasible(s, tol, dim, type_, is_float, N)
+    modes = (C.c_int64 * 3)(256, 256, 256)
+    assert lib.b200_host_choose_sigma(1e-6, 3, 1, 1, modes, 1e8) == 2.0      # C3: spread-dominated
+    s = lib.b200_host_choose_sigma(1e-4, 3, 1, 1, modes, 1e4)                # 1e4 points on 512^3
+    assert 1.15 <= s < 2.0 and lib.b200_host_sigma_feasible(s, 1e-4, 3, 1, 1, 256.0)
+    modes2 = (C.c_int64 * 3)(512, 512, 1)
+    s = lib.b200_host_choose_sigma(1e-9, 2, 1, 0, modes2, 2e3)
+    assert 1.2 <= s < 2.0 and lib.b200_host_sigma_feasible(s, 1e-9, 2, 1, 0, 512.0)
+    assert lib.b200_host_choose_sigma(1e-9, 2, 1, 0, modes2, 1e7) == 2.0     # C4
