@@ -28,7 +28,7 @@ def _declared_symbols():
                     for p in ("", "f"):
                         names.add(f"{stem}{p}{m.group(1)}")
         text = re.sub(r"#define B200_\w+_SIMPLE\(.*?\n(?=B200_)", "", text, flags=re.S)
-        for m in re.finditer(r"^\s*(?:int|void|int64_t|const char \*)\s*\*?(\w+)\(", text, re.M):
+        for m in re.finditer(r"^\s*(?:int|void|int64_t|double|const char \*)\s*\*?(\w+)\(", text, re.M):
             names.add(m.group(1))
     return names
 
