@@ -78,3 +78,54 @@ class BatchSplit:
         parts = [torch.empty_like(buf) for _ in range(self.world)]
         self.dist.all_gather(parts, buf, group=self.group)
         return torch.cat([p[: hi - lo] for p, (lo, hi) in zip(parts, self.slices)], dim=0)
+
+
+class TargetSplit:
+    """Type 3 (nonuniform -> nonuniform) over the ranks of a process group.
+
+    The outputs of a type-3 transform are independent given the sources: f_k = sum_j c_j
+    exp(+-i s_k . x_j) (include/finufft/execute.hpp:432-558), so the N target frequencies are split
+    into contiguous slices, every rank keeps all M sources and evaluates its slice with an
+    ordinary type-3 plan on its own GPU: no data-path collective, outputs stay sharded (or one
+    all_gather when every rank wants all of them).  Each rank's plan chooses its own spreading
+    grid from the extent of ITS targets (setpts.hpp:163-319), which only shrinks the work.
+    (The finer decomposition of SURVEY.md 8(e) - outer spread on z-slabs, a slab -> block
+    transpose of the spreading grid, a sharded inner type 2 - is not built.)
+
+    make_plan() -> object with setpts(*src, s=.., t=.., u=..) and execute(c) (a type-3
+    finufft_b200.Plan on this rank's GPU).
+    """
+
+    def __init__(self, n_targets: int, make_plan: Callable, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_targets = n_targets
+        self.slices = split_transforms(n_targets, self.world)
+        self.lo, self.hi = self.slices[self.rank]
+        self.plan = make_plan() if self.hi > self.lo else None
+
+    def setpts(self, sources, targets):
+        """sources, targets: sequences of coordinate arrays in the plan's own argument order;
+        the targets are the FULL arrays, this rank keeps [lo, hi)."""
+        if self.plan is not None:
+            names = ("s", "t", "u")[: len(targets)]
+            self.plan.setpts(*sources, **{n: a[self.lo:self.hi].contiguous()
+                                          for n, a in zip(names, targets)})
+
+    def execute_local(self, c):
+        return None if self.plan is None else self.plan.execute(c)
+
+    def execute_gathered(self, c):
+        import torch
+        mine = self.execute_local(c)
+        if self.world == 1:
+            return mine
+        nmax = max(hi - lo for lo, hi in self.slices)
+        buf = torch.zeros((nmax,), dtype=c.dtype, device=c.device)
+        if mine is not None:
+            buf[: mine.shape[0]] = mine
+        parts = [torch.empty_like(buf) for _ in range(self.world)]
+        self.dist.all_gather(parts, buf, group=self.group)
+        return torch.cat([p[: hi - lo] for p, (lo, hi) in zip(parts, self.slices)], dim=0)

@@ -81,3 +81,64 @@ def test_batch_split_two_ranks_gloo(ntr):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+class _OracleType3:
+    """CPU stand-in with the interface of a type-3 finufft_b200.Plan: the oracle's own type 3."""
+
+    def __init__(self, dim, tol):
+        from oracle import oracle as O
+        self.O, self.dim, self.tol, self.p = O, dim, tol, None
+
+    def setpts(self, *src, s=None, t=None, u=None):
+        import numpy as np
+        O = self.O
+        self.p = O.Plan(3, [1] * self.dim, 1, 1, self.tol, np.float64, nthr=1, dim=self.dim)
+        frq = [a for a in (s, t, u) if a is not None]
+        # python order (slowest first) -> library order, like finufft_b200.Plan.setpts
+        pts = [a.numpy() for a in src][::-1] + [None] * (3 - self.dim)
+        fr = [a.numpy() for a in frq][::-1] + [None] * (3 - self.dim)
+        self.p.setpts(*pts, *fr)
+
+    def execute(self, c):
+        return torch.from_numpy(self.p.execute(c.numpy()))
+
+
+def _worker_t3(rank, world, port, q):
+    import numpy as np
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from finufft_b200.parallel import TargetSplit
+    from oracle import oracle as O
+    rng = np.random.default_rng(4)
+    M, N, tol = 3000, 2501, 1e-9
+    src = [torch.from_numpy(rng.uniform(-np.pi, np.pi, M)) for _ in range(2)]
+    tgt = [torch.from_numpy(25.0 * rng.uniform(-1, 1, N) + sh) for sh in (3.0, -7.0)]
+    c = torch.from_numpy(rng.standard_normal(M) + 1j * rng.standard_normal(M))
+    ts = TargetSplit(N, lambda: _OracleType3(2, tol))
+    ts.setpts(src, tgt)
+    full = ts.execute_gathered(c)
+    want = O.dirft(3, src[1].numpy(), src[0].numpy(), None, c.numpy(), 1,
+                   s=tgt[1].numpy(), t=tgt[0].numpy())
+    err = float(np.linalg.norm(full.numpy() - want) / np.linalg.norm(want))
+    q.put((rank, bool(err < 1e-8 and full.shape[0] == N)))
+    dist.destroy_process_group()
+
+
+def test_type3_target_split_two_ranks_gloo():
+    """Type 3 sharded by targets (finufft_b200/parallel.py::TargetSplit), world size 2 over gloo,
+    the oracle's type 3 as the local plan, against the reference's direct sum."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_t3, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
