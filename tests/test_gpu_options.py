@@ -188,7 +188,18 @@ def test_auto_upsampfac_host_api(cuda, oracle, prec, tol, dim, modes, M):
         op = _checker(oracle)(type_, list(modes[::-1]), 1, 1, tol, rt, sigma=sigma, nthr=4)
         op.setpts(*(pts[::-1] + [None] * (3 - dim)))
         assert op.ns == hp.info()["ns"] and op.nf == hp.info()["nf"]
-        assert oracle.relerr(got, op.execute(data)) <= 2 * tol, (type_, sigma)
-        # a second, dense point set on the same plan: sigma is chosen again
+        want = op.execute(data)
+        # At the smallest feasible sigma the aliasing error itself sits at the tolerance and
+        # 1/phihat amplifies the last bits of the window fit at the edge modes, so two correct
+        # implementations differ by ~2*tol (measured 2.03e-9 at tol 1e-9, sigma 1.2027).  Bars:
+        # within 4*tol of the reference library, and as close to the direct sum as it is.
+        assert oracle.relerr(got, want) <= 4 * tol, (type_, sigma)
+        lp = pts[::-1] + [None] * (3 - dim)
+        truth = oracle.dirft(type_, lp[0], lp[1], lp[2], data.reshape(-1), 1,
+                             n_modes=list(modes[::-1]))
+        e_gpu, e_ref = oracle.relerr(got, truth), oracle.relerr(want, truth)
+        print(f"\n[auto sigma {sigma:.4f} type {type_}] gpu-vs-direct {e_gpu:.2e}  "
+              f"reference-vs-direct {e_ref:.2e}")
+        assert e_gpu <= max(2 * tol, 1.5 * e_ref), (type_, sigma, e_gpu, e_ref)
         hp.destroy()
         op.destroy()
