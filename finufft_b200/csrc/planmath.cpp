@@ -354,7 +354,7 @@ int width_at(double tol, int dim, int type, double sigma, bool is_float) {
   if (choose_kernel(tol, dim, type, sigma, is_float, true, ns, beta, tu)) return 16;
   return ns;
 }
-// milliseconds of one execute on a B200 (measured: profiles/r2g_bench_*.json)
+// milliseconds of one execute on a B200 (measured: profiles/r2z_bench_*.json)
 double cost_ms(int dim, bool is_float, const int64_t *modes, double sigma, int ns, double M) {
   double cells = 1.0, stencil = 1.0;
   for (int d = 0; d < dim; ++d) {

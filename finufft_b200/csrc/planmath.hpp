@@ -82,7 +82,7 @@ double smallest_feasible_sigma(double tol, int dim, int type, bool is_float, dou
 // heuristic (include/finufft/heuristics.hpp:82-128: the smallest feasible sigma, then for every
 // narrower kernel width the smallest sigma that reaches it, up to 2.5), scored with a B200 cost
 // model (spread / interp time per point by dimension, width, precision and kernel family + FFT
-// and grid-pass time per fine-grid cell; constants from profiles/r2g_bench_*.json).
+// and grid-pass time per fine-grid cell; constants from profiles/r2z_bench_*.json).
 double choose_sigma(double tol, int dim, int type, bool is_float, const int64_t *modes,
                     double npoints);
 

@@ -13,7 +13,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r2g"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2z"
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 for f in glob.glob(os.path.join(G, f"{tag}_bench_*.json")) + glob.glob(os.path.join(G, f"{tag}_bench_*.txt")):

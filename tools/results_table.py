@@ -1,7 +1,7 @@
 """Markdown table of the bench lines in profiles/<tag>_bench_*.json (for DESIGN.md section 5)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r2g"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2z"
 rows = [("c3_t1", "C3 type 1 (headline)"), ("c3_t2", "C3 type 2"), ("c3_t1_cluster", "C3 type 1, clustered"),
         ("c3_t2_cluster", "C3 type 2, clustered"), ("c2_t2", "C2 type 2"), ("c2_t1", "2D 2048², M=1e8, type 1"),
         ("c4_t1", "C4 type 1, ntransf = 64 (ms per 64 vectors; kernel = per vector)"), ("c2_t2_cluster", "C2 type 2, clustered"), ("c1_t1", "C1 type 1 (1D, double)")]

@@ -3,7 +3,7 @@ profiles/<tag>_bench_*.json.   python tools/scaling_table.py [1gpu-tag]"""
 import glob, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = os.path.join(ROOT, "profiles")
-one = sys.argv[1] if len(sys.argv) > 1 else "r2g"
+one = sys.argv[1] if len(sys.argv) > 1 else "r2z"
 
 
 def load(p):
