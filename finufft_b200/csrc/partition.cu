@@ -112,6 +112,28 @@ k_bin_hist(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict
   }
 }
 
+// Every `step`-th point only: a cheap look at the distribution before the full passes.
+template<class T, int DIM>
+__global__ void __launch_bounds__(256)
+k_bin_hist_sample(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
+                  uint32_t M, uint32_t step, GridGeom<T> g, uint32_t *__restrict__ cnt) {
+  const uint32_t n      = M / step;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const uint32_t i = k * step;
+    atomicAdd(&cnt[bin_key_of<T, DIM>(x[i], DIM > 1 ? y[i] : (T)0, DIM > 2 ? z[i] : (T)0, i, g)], 1u);
+  }
+}
+__global__ void __launch_bounds__(256)
+k_max_u32(const uint32_t *__restrict__ v, uint32_t n, uint32_t *__restrict__ out) {
+  uint32_t mx           = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) mx = max(mx, v[i]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
+}
+
 // ------------------------------------------------------------------------------ 2. segments
 __global__ void k_seg_prep(const uint32_t *__restrict__ binstart, uint32_t nbins, int ss, int sb,
                            uint32_t nseg, uint32_t nA, uint32_t *__restrict__ cursorB,
@@ -383,6 +405,20 @@ static bool partition_sort_dim(const T *x, const T *y, const T *z, uint32_t M,
       cursorA(pp.nA, st, device), dmax(1, st, device);
   cu(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * nbins, st));
   cu(cudaMemsetAsync(dmax.p, 0, sizeof(uint32_t), st));
+  if (M >= (1u << 22)) {
+    // Clustered input cannot take this path (a segment must fit shared memory) and its full
+    // histogram is expensive (same-address atomics): look at 65536 evenly spaced points first
+    // and leave at once when a single bin alone would overflow a segment.
+    const uint32_t step = M >> 16;
+    k_bin_hist_sample<T, DIM><<<64, 256, 0, st>>>(x, y, z, M, step, g, cnt.p);
+    k_max_u32<<<blocks_for(nbins, 256, 4), 256, 0, st>>>(cnt.p, nbins, dmax.p);
+    uint32_t seen = 0;
+    cu(cudaMemcpyAsync(&seen, dmax.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    cu(cudaStreamSynchronize(st));
+    if ((uint64_t)seen * step > 2ull * SegCap<T>::value && seen >= 8) return false;
+    cu(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * nbins, st));
+    cu(cudaMemsetAsync(dmax.p, 0, sizeof(uint32_t), st));
+  }
   k_bin_hist<T, DIM><<<blocks_for(M, 256, 8), 256, 0, st>>>(x, y, z, M, g, cnt.p);
   exclusive_scan_u32(cnt.p, binstart, nbins, scan_tmp, st);
   k_seg_prep<<<blocks_for(pp.nseg, 256, 8), 256, 0, st>>>(binstart, nbins, pp.ss, pp.sb, pp.nseg,

@@ -60,8 +60,9 @@ struct PartPlan {
 PartPlan plan_partition(uint64_t M, uint32_t nbins, int cls, int ns, bool is_double, bool force);
 
 // Runs the whole sort.  binstart (nbins+1), xs/ys/zs/sidx (M) are outputs.  Returns false, with
-// only binstart written, when a segment holds more than SegCap<T>::value points; the caller then
-// takes the counting-sort path.  Synchronises the stream once.
+// nothing the caller may rely on written, when a segment holds more than SegCap<T>::value points
+// (seen on a 65536-point sample first, so that clustered input leaves before the full histogram);
+// the caller then takes the counting-sort path.  Synchronises the stream once or twice.
 template<class T>
 bool partition_sort(int dim, const T *x, const T *y, const T *z, uint32_t M,
                     const GridGeom<T> &g, const PartPlan &pp, uint32_t *binstart, T *xs, T *ys,
