@@ -105,3 +105,34 @@ def test_auto_upsampfac_search_matches_reference():
     s = lib.b200_host_choose_sigma(1e-9, 2, 1, 0, modes2, 2e3)
     assert 1.2 <= s < 2.0 and lib.b200_host_sigma_feasible(s, 1e-9, 2, 1, 0, 512.0)
     assert lib.b200_host_choose_sigma(1e-9, 2, 1, 0, modes2, 1e7) == 2.0     # C4
+
+
+def test_bench_input_streams_are_the_reference_perftest_streams(tmp_path):
+    """tools/perfdata.py (bench inputs) against the reference's own generator compiled from where
+    it lies (perftest/randunif.h:29-73), when /root/reference is present; always: determinism,
+    independence of the chunk offset, value range."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import perfdata
+    a = np.empty(200_000, dtype=np.float32)
+    perfdata.fill(a, "X", np.float32(np.pi), 0.0)
+    b = np.empty(70_000, dtype=np.float32)
+    perfdata.fill(b, "X", np.float32(np.pi), 0.0, first=65_000)
+    assert np.array_equal(a[65_000:135_000], b)
+    assert a.min() >= -np.pi and a.max() <= np.pi and abs(a.mean()) < 0.02
+    d = np.empty(1000, dtype=np.float64)
+    perfdata.fill(d, "C")
+    assert np.all(np.abs(d) < 1.0)
+    hdr = "/root/reference/perftest/randunif.h"
+    if not os.path.exists(hdr):
+        return
+    src = tmp_path / "ru.cpp"
+    src.write_text('#include "%s"\n#include <cstdio>\nint main(){ std::vector<float> v(200000);'
+                   ' perftest_rand::fill<float>(v.data(), (std::int64_t)v.size(), perftest_rand::X,'
+                   ' 3.14159265358979323846f, 0.f);'
+                   ' fwrite(v.data(), 4, v.size(), stdout); }\n' % hdr)
+    exe = tmp_path / "ru"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", str(src), "-o", str(exe)])
+    ref = np.frombuffer(subprocess.check_output([str(exe)]), dtype=np.float32)
+    assert np.array_equal(ref, a)
