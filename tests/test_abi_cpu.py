@@ -132,7 +132,8 @@ def test_c_caller_compiles_links_and_gets_the_no_device_code(tmp_path):
     # headers are valid C++ too
     cpp = tmp_path / "hdr.cpp"
     cpp.write_text('#include "b200_finufft.h"\n#include "b200_cufinufft.h"\n'
-                   '#include "b200_introspect.h"\nint main() { return 0; }\n')
+                   '#include "b200_introspect.h"\n#include "b200_sharded.h"\n'
+                   'int main() { return 0; }\n')
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
                            str(cpp)])
     try:
@@ -142,3 +143,14 @@ def test_c_caller_compiles_links_and_gets_the_no_device_code(tmp_path):
         has_gpu = False
     rc = subprocess.call([exe])
     assert rc == (0 if has_gpu else 15)
+    # the sharded entry points from C (examples/sharded3d1f.c), when the CUDA runtime is there
+    cuda_inc, cuda_lib = "/usr/local/cuda/include", "/usr/local/cuda/lib64"
+    if os.path.exists(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        exe2 = str(tmp_path / "sharded3d1f")
+        subprocess.check_call(["gcc", "-std=c99", "-D_GNU_SOURCE", "-O1", "-Wall", "-Werror", "-I",
+                               os.path.join(ROOT, "include"), "-I", cuda_inc,
+                               os.path.join(ROOT, "examples", "sharded3d1f.c"), "-L", libdir,
+                               "-lfinufft_b200", "-L", cuda_lib, "-lcudart", "-lm",
+                               f"-Wl,-rpath,{libdir}", "-o", exe2])
+        rc = subprocess.call([exe2])
+        assert rc == (0 if has_gpu else 15)
