@@ -35,3 +35,24 @@ def test_reference_api_program(cuda, prog):
     if r.returncode == 77:
         pytest.skip(f"{prog}: skipped by the program itself (needs 2 GPUs)\n{tail}")
     assert r.returncode == 0, f"{prog} exited with {r.returncode}\n{tail}"
+
+
+@pytest.mark.parametrize("pkg", ["cufinufft", "finufft"])
+def test_reference_python_suites(cuda, pkg):
+    """The reference's own pytest suites (python/cufinufft/tests, python/finufft/test: 2927 + 659
+    cases, unmodified) with its ctypes bindings loading THIS library under the reference's
+    library file name.  tools/ref_pytests.py stages the packages into oracle/_ref/py/ in the
+    container that holds /root/reference; they travel with the snapshot."""
+    import sys
+    staged = os.path.join(ROOT, "oracle", "_ref", "py", pkg)
+    if not os.path.isdir(staged):
+        if os.path.isdir("/root/reference/python"):
+            subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ref_pytests.py"),
+                                   "stage"])
+        else:
+            pytest.skip("oracle/_ref/py not staged (needs /root/reference at build time)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_pytests.py"), "run",
+                        "--which", pkg], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    print(r.stdout[-600:])
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
