@@ -91,7 +91,8 @@ SIMPLE_GPU = [f"cufinufft{p}{d}d{t}{m}" for p in ("", "f") for d in (1, 2, 3)
               for t in (1, 2, 3) for m in ("", "many")]
 SIMPLE_HOST = [f"finufft{p}{d}d{t}{m}" for p in ("", "f") for d in (1, 2, 3)
                for t in (1, 2, 3) for m in ("", "many")]
-INTROSPECT = ["b200_get_plan_info", "b200_get_sort_permutation", "b200_get_raw_sort_order",
+INTROSPECT = ["b200_get_plan_info", "b200_get_inner_plan_info", "b200_host_sigma_candidates",
+              "b200_host_choose_sigma_type3", "b200_get_sort_permutation", "b200_get_raw_sort_order",
               "b200_get_sort_path", "b200_get_window_table",
               "b200_get_phihat", "b200_enable_profiling", "b200_get_stage_ms",
               "b200_get_launch_count", "b200_host_kernel", "b200_host_fine_grid",
@@ -150,6 +151,8 @@ def load():
         de.restype = ci
     lib.b200_get_plan_info.argtypes = [vp, C.POINTER(PlanInfo)]
     lib.b200_get_plan_info.restype = ci
+    lib.b200_get_inner_plan_info.argtypes = [vp, C.POINTER(PlanInfo)]
+    lib.b200_get_inner_plan_info.restype = ci
     lib.b200_get_sort_permutation.argtypes = [vp, vp]
     lib.b200_get_sort_permutation.restype = ci
     lib.b200_get_raw_sort_order.argtypes = [vp, vp]
@@ -177,6 +180,12 @@ def load():
     lib.b200_host_sigma_feasible.restype = ci
     lib.b200_host_choose_sigma.argtypes = [dbl, ci, ci, ci, C.POINTER(i64), dbl]
     lib.b200_host_choose_sigma.restype = dbl
+    lib.b200_host_sigma_candidates.argtypes = [dbl, ci, ci, ci, dbl, dbl, C.POINTER(dbl),
+                                               C.POINTER(ci), ci]
+    lib.b200_host_sigma_candidates.restype = ci
+    lib.b200_host_choose_sigma_type3.argtypes = [dbl, ci, ci, dbl, dbl, C.POINTER(dbl),
+                                                 C.POINTER(dbl)]
+    lib.b200_host_choose_sigma_type3.restype = dbl
     lib.b200_host_fseries.argtypes = [i64, ci, ci, ci, vp, vp]
     lib.b200_host_fseries.restype = ci
     lib.b200_version.restype = C.c_char_p

@@ -438,9 +438,8 @@ int host_simple(int dim, int type, int ntr, int64_t M, const T *x, const T *y, c
   return err;
 }
 
-template<class T> void fill_info(DevicePlan<T> *p, b200_plan_info *out) {
-  const Engine<T> &e = p->eng;
-  out->is_float = p->is_float;
+template<class T> void fill_info(const Engine<T> &e, b200_plan_info *out) {
+  out->is_float = std::is_same<T, float>::value;
   out->type  = e.type;
   out->dim   = e.dim;
   out->ntr   = e.ntr;
@@ -732,8 +731,23 @@ int b200_get_plan_info(void *plan, b200_plan_info *out) {
   return guarded([&] {
     auto *b = static_cast<PlanBase *>(plan);
     if (!b || b->magic != kMagic || !out) throw Failure{ERR_PLAN_NOTVALID};
-    if (b->is_float) fill_info<float>(as_plan<float>(plan), out);
-    else fill_info<double>(as_plan<double>(plan), out);
+    if (b->is_float) fill_info<float>(as_plan<float>(plan)->eng, out);
+    else fill_info<double>(as_plan<double>(plan)->eng, out);
+  });
+}
+int b200_get_inner_plan_info(void *plan, b200_plan_info *out) {
+  return guarded([&] {
+    auto *b = static_cast<PlanBase *>(plan);
+    if (!b || b->magic != kMagic || !out) throw Failure{ERR_PLAN_NOTVALID};
+    if (b->is_float) {
+      const Engine<float> *in = as_plan<float>(plan)->eng.inner();
+      if (!in) throw Failure{ERR_PLAN_NOTVALID};
+      fill_info<float>(*in, out);
+    } else {
+      const Engine<double> *in = as_plan<double>(plan)->eng.inner();
+      if (!in) throw Failure{ERR_PLAN_NOTVALID};
+      fill_info<double>(*in, out);
+    }
   });
 }
 int b200_get_sort_permutation(void *plan, uint32_t *host_out) {
@@ -849,6 +863,14 @@ int b200_host_sigma_feasible(double sigma, double tol, int dim, int type, int is
 double b200_host_choose_sigma(double tol, int dim, int type, int is_float, const int64_t *modes,
                               double npoints) {
   return choose_sigma(tol, dim, type, is_float != 0, modes, npoints);
+}
+int b200_host_sigma_candidates(double tol, int dim, int type, int is_float, double maxN,
+                               double smax, double *sigma_out, int *ns_out, int cap) {
+  return sigma_candidates(tol, dim, type, is_float != 0, maxN, smax, sigma_out, ns_out, cap);
+}
+double b200_host_choose_sigma_type3(double tol, int dim, int is_float, double nsources,
+                                    double ntargets, const double *X, const double *S) {
+  return choose_sigma_type3(tol, dim, is_float != 0, nsources, ntargets, X, S);
 }
 int64_t b200_host_fine_grid(double sigma, int64_t modes, int ns) {
   return fine_grid_size(sigma, modes, ns);

@@ -130,7 +130,7 @@ Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr
   pool_held_ = true;
   tol = tol_req_ = tol_;
   sigma = opts.upsampfac == 0.0 ? 2.0 : opts.upsampfac;
-  if (opts.upsampfac != 0.0 || type == 3 || opts.spreadinterponly) opts.auto_sigma = 0;
+  if (opts.upsampfac != 0.0 || opts.spreadinterponly) opts.auto_sigma = 0;
   batch = opts.maxbatch > 0 ? std::min(opts.maxbatch, ntr) : std::min(ntr, 8);
   if (opts.maxsub < 32) opts.maxsub = 32;
   if (const char *env = getenv("B200_NUFFT_SWEEP")) opts.sweep = atoi(env);  // debugging aids
@@ -387,6 +387,9 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
     uint32_t k = (uint32_t)want_groups_;
     if (type == 3 || M < 2 * (int64_t)k || (uint64_t)geom.nbins1 * k > 0x7fffffffull) k = 1;
     geom.nchunks   = k;
+    // equal groups: sizes shrinking geometrically towards the last group (so that the spread no
+    // upload hides is short) were measured slower at C3, 22.0 -> 24.2 ms (ratio 0.65) and
+    // 23.1 ms (0.8), type 2 25.8 -> 27.5 ms (profiles/r2_e2e_group_layouts.txt)
     geom.chunk_len = k > 1 ? (uint32_t)((M + k - 1) / k) : 0xffffffffu;
     geom.nbins     = geom.nbins1 * k;
   }

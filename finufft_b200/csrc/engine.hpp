@@ -100,6 +100,7 @@ template<class T> class Engine {
   // split the next setpts into k groups of consecutive user indices (types 1 and 2 only)
   void set_point_groups(int k) { want_groups_ = k < 1 ? 1 : (k > 16 ? 16 : k); }
   int point_groups() const { return (int)geom.nchunks; }
+  const Engine<T> *inner() const { return inner_.get(); }  // type 3: the inner type-2 plan
   int64_t group_len() const { return (int64_t)geom.chunk_len; }
 
   // ---- introspection (tests, benches) ----

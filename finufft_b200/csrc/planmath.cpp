@@ -354,13 +354,11 @@ int width_at(double tol, int dim, int type, double sigma, bool is_float) {
   if (choose_kernel(tol, dim, type, sigma, is_float, true, ns, beta, tu)) return 16;
   return ns;
 }
-// milliseconds of one execute on a B200 (measured: profiles/r2z_bench_*.json)
-double cost_ms(int dim, bool is_float, const int64_t *modes, double sigma, int ns, double M) {
-  double cells = 1.0, stencil = 1.0;
-  for (int d = 0; d < dim; ++d) {
-    cells *= (double)fine_grid_size(sigma, modes[d], ns);
-    stencil *= ns;
-  }
+// Cost model of one execute on a B200, milliseconds (measured: profiles/r2z_bench_*.json).
+// spread / interp of M points with a width-ns kernel:
+double spread_ms(int dim, bool is_float, int ns, double M) {
+  double stencil = 1.0;
+  for (int d = 0; d < dim; ++d) stencil *= ns;
   double base, per_cell;  // ms per point: base + per_cell * ns^dim
   if (dim == 3) {
     const bool sweep = is_float && ns <= 7;            // k_sweep3: 8.05 ms per 1e8 points at ns = 7
@@ -372,44 +370,107 @@ double cost_ms(int dim, bool is_float, const int64_t *modes, double sigma, int n
   } else {
     base = 2.0e-8, per_cell = is_float ? 1.4e-9 : 2.7e-9;  // generic 1D: 4.7 ms per 1e8 (f64, ns 10)
   }
-  const double spread = M * (base + per_cell * stencil);
-  // cuFFT + the zero / deconvolve passes over the grid: 1.08 + 0.27 ms on 512^3 (f32)
-  const double fft = cells * std::log2(std::max(cells, 2.0)) * 3.0e-10 * (is_float ? 1.0 : 2.0) +
-                     cells * 2.0e-9 * (is_float ? 1.0 : 2.0);
-  return spread + fft;
+  return M * (base + per_cell * stencil);
+}
+// cuFFT + the zero / deconvolve passes over a fine grid: 1.08 + 0.27 ms on 512^3 (f32)
+double grid_ms(double cells, bool is_float) {
+  const double w = is_float ? 1.0 : 2.0;
+  return cells * std::log2(std::max(cells, 2.0)) * 3.0e-10 * w + cells * 2.0e-9 * w;
+}
+double cost_ms(int dim, bool is_float, const int64_t *modes, double sigma, int ns, double M) {
+  double cells = 1.0;
+  for (int d = 0; d < dim; ++d) cells *= (double)fine_grid_size(sigma, modes[d], ns);
+  return spread_ms(dim, is_float, ns, M) + grid_ms(cells, is_float);
+}
+double working_tol(double tol, bool is_float) {
+  const double eps = is_float ? (double)std::numeric_limits<float>::epsilon()
+                              : std::numeric_limits<double>::epsilon();
+  const double t = is_float ? (double)(float)tol : tol;
+  return t < eps ? eps : t;
+}
+// The minimiser over the candidate set, with this library's two house rules: candidates stop at
+// sigma = 2 (the reference searches up to 2.5; above 2 the fine grid grows faster than the kernel
+// narrows on this device, and 2 is where every kernel family is tuned), and sigma = 2 is kept
+// unless another candidate is clearly (by the factor `margin`) cheaper.  cost(sigma, ns) in milliseconds.
+template<class Cost>
+double pick_sigma(double t, int dim, int type, bool is_float, double maxN, Cost &&cost,
+                  double margin, double *cost_out = nullptr) {
+  constexpr double smax = 2.0;
+  double sig[32];
+  int wid[32];
+  const int n = sigma_candidates(t, dim, type, is_float, maxN, smax, sig, wid, 32);
+  // tolerance out of reach, or nothing below the cap: the default
+  if (n == 0 || sig[0] >= smax || !sigma_feasible(sig[0], t, dim, type, is_float, maxN)) {
+    if (cost_out) *cost_out = cost(smax, width_at(t, dim, type, smax, is_float));
+    return smax;
+  }
+  double best = smax, best_cost = std::numeric_limits<double>::infinity();
+  for (int i = 0; i < n; ++i) {
+    const double c = cost(sig[i], wid[i]);
+    if (c < best_cost) best = sig[i], best_cost = c;
+  }
+  if (sigma_feasible(2.0, t, dim, type, is_float, maxN)) {
+    const double c2 = cost(2.0, width_at(t, dim, type, 2.0, is_float));
+    if (c2 <= margin * best_cost) best = 2.0, best_cost = c2;
+  }
+  if (cost_out) *cost_out = best_cost;
+  return best;
 }
 }  // namespace
 
+int sigma_candidates(double tol, int dim, int type, bool is_float, double maxN, double smax,
+                     double *sigma_out, int *ns_out, int cap) {
+  int n = 0;
+  auto push = [&](double s) {
+    if (n < cap) sigma_out[n] = s, ns_out[n] = width_at(tol, dim, type, s, is_float), ++n;
+  };
+  const double smin = smallest_feasible_sigma(tol, dim, type, is_float, maxN);
+  push(smin);
+  if (!sigma_feasible(smin, tol, dim, type, is_float, maxN) || smin >= smax) return n;
+  const int ns_lo = width_at(tol, dim, type, smax, is_float);
+  for (int w = width_at(tol, dim, type, smin, is_float) - 1; w >= ns_lo; --w) {
+    // sigma_reaching sits exactly on the edge of the width law's ceil(); one part in 1e12 above
+    // it the width is w whatever the rounding of the log / sqrt did
+    const double edge = sigma_reaching(tol, dim, type, w) * (1.0 + 1e-12);
+    const double s    = std::min(std::max(edge, smin), smax);
+    if (sigma_feasible(s, tol, dim, type, is_float, maxN)) push(s);
+  }
+  return n;
+}
+
 double choose_sigma(double tol, int dim, int type, bool is_float, const int64_t *modes,
-                    double npoints) {
-  const double eps = is_float ? (double)std::numeric_limits<float>::epsilon()
-                              : std::numeric_limits<double>::epsilon();
-  double t = is_float ? (double)(float)tol : tol;
-  if (t < eps) t = eps;
+                    double npoints, double *cost_out) {
+  const double t = working_tol(tol, is_float);
   double maxN = 1.0;
   for (int d = 0; d < dim; ++d) maxN = std::max(maxN, (double)modes[d]);
-  const double smin = smallest_feasible_sigma(t, dim, type, is_float, maxN);
-  if (!sigma_feasible(smin, t, dim, type, is_float, maxN)) return 2.0;  // tol out of reach: default
-  double best = smin;
-  double best_cost = cost_ms(dim, is_float, modes, smin, width_at(t, dim, type, smin, is_float), npoints);
-  // candidates stop at sigma = 2 (the reference searches up to 2.5; above 2 the fine grid grows
-  // faster than the kernel narrows on this device, and 2 is where every kernel family is tuned)
-  constexpr double smax = 2.0;
-  if (smin >= smax) return smax;
-  const int ns_lo = width_at(t, dim, type, smax, is_float);
-  for (int w = width_at(t, dim, type, smin, is_float) - 1; w >= ns_lo; --w) {
-    const double s = std::min(std::max(sigma_reaching(t, dim, type, w), smin), smax);
-    if (!sigma_feasible(s, t, dim, type, is_float, maxN)) continue;
-    const double c = cost_ms(dim, is_float, modes, s, width_at(t, dim, type, s, is_float), npoints);
-    if (c < best_cost) best = s, best_cost = c;
-  }
-  // sigma = 2 is the value every kernel family is tuned and tested at: prefer it unless another
-  // candidate is clearly (> 10 %) cheaper
-  if (sigma_feasible(2.0, t, dim, type, is_float, maxN)) {
-    const double c2 = cost_ms(dim, is_float, modes, 2.0, width_at(t, dim, type, 2.0, is_float), npoints);
-    if (c2 <= 1.1 * best_cost) return 2.0;
-  }
-  return best;
+  return pick_sigma(
+      t, dim, type, is_float, maxN,
+      [&](double s, int ns) { return cost_ms(dim, is_float, modes, s, ns, npoints); }, 1.1,
+      cost_out);
+}
+
+double choose_sigma_type3(double tol, int dim, bool is_float, double nsources, double ntargets,
+                          const double *X, const double *S) {
+  const double t = working_tol(tol, is_float);
+  auto cost = [&](double s3, int ns3) {
+    int64_t nfd[3] = {1, 1, 1};
+    double cells   = 1.0;
+    for (int d = 0; d < dim; ++d) {
+      double h, gam;
+      type3_grid(s3, X[d], S[d], ns3, nfd[d], h, gam);
+      cells *= (double)nfd[d];
+    }
+    double inner = 0.0;  // the inner type 2 re-optimises its own sigma from nfd and the targets
+    choose_sigma(t, dim, 2, is_float, nfd, ntargets, &inner);
+    // outer spread + zero fill of the spreading grid (one write pass) + inner transform
+    return spread_ms(dim, is_float, ns3, nsources) + cells * 1.3e-9 * (is_float ? 1.0 : 2.0) +
+           inner;
+  };
+  // A wider margin than for types 1 / 2: the model knows cuFFT by cell count only, and at C5
+  // (M = N = 1e7, tol 1e-6) the candidate it scored 11 % cheaper (sigma3 = 1.937: grids 432^3 /
+  // 864^3 instead of 450^3 / 900^3) measured 11 % slower; the picks that matter (few points on a
+  // wide frequency box, FFT-dominated) are cheaper by integer factors.
+  return pick_sigma(t, dim, 3, is_float, 1.0, cost, 1.25);
 }
 
 // ------------------------------------------------------------------ type 3

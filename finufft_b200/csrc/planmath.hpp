@@ -83,8 +83,22 @@ double smallest_feasible_sigma(double tol, int dim, int type, bool is_float, dou
 // narrower kernel width the smallest sigma that reaches it, up to 2.5), scored with a B200 cost
 // model (spread / interp time per point by dimension, width, precision and kernel family + FFT
 // and grid-pass time per fine-grid cell; constants from profiles/r2z_bench_*.json).
+// cost_out (optional): the model's milliseconds for the value returned.
 double choose_sigma(double tol, int dim, int type, bool is_float, const int64_t *modes,
-                    double npoints);
+                    double npoints, double *cost_out = nullptr);
+// The candidate set itself, in the reference's order (heuristics.hpp:82-107 `minimize`): the
+// smallest feasible sigma, then for every narrower width down to the width at smax the smallest
+// sigma reaching it (clamped to [smin, smax], infeasible ones skipped); with smax = 2.5 these are
+// exactly the (sigma, ns) pairs the reference's minimiser scores.  Returns the count.
+int sigma_candidates(double tol, int dim, int type, bool is_float, double maxN, double smax,
+                     double *sigma_out, int *ns_out, int cap);
+// Automatic upsampfac of a type-3 plan (include/finufft/heuristics.hpp:130-150 `best_type3`,
+// applied at setpts: include/finufft/setpts.hpp:186-200): candidates as above with type = 3,
+// cost = outer spread of the sources at the candidate's width + the inner type-2 transform on the
+// grid that sigma builds from the half-widths X (sources) and S (targets), the inner transform at
+// ITS best sigma for the number of targets; this device's cost model.
+double choose_sigma_type3(double tol, int dim, bool is_float, double nsources, double ntargets,
+                          const double *X, const double *S);
 
 // Type-3 fine grid (nf, spacing h, rescale gam) for half-widths X (space) and S (frequency).
 void type3_grid(double sigma, double X, double S, int ns, int64_t &nf, double &h, double &gam);

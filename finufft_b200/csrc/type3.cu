@@ -193,6 +193,22 @@ void Engine<T>::setpts_type3(int64_t M_, const T *x, const T *y, const T *z, int
     if (M == 0) X[d] = 0, t3C_[d] = 0;
     if (N == 0) S[d] = 0, t3D_[d] = 0;
   }
+  if (opts.auto_sigma) {
+    // upsampfac = 0 on the host API: sigma3 from the half-widths and the point counts, as the
+    // reference CPU library does here (include/finufft/setpts.hpp:186-200); the inner type 2
+    // below then picks its own sigma from its grid and the number of targets (:302-304)
+    const double Xd[3] = {(double)X[0], (double)X[1], (double)X[2]};
+    const double Sd[3] = {(double)S[0], (double)S[1], (double)S[2]};
+    const double s_new = choose_sigma_type3(tol_req_, dim, std::is_same<T, float>::value,
+                                            (double)M, (double)N, Xd, Sd);
+    if (std::abs(s_new - sigma) > 1e-12) {
+      cu(cudaStreamSynchronize(st));
+      sigma = s_new;
+      tol   = tol_req_;
+      plan_kernel();
+      coef_dev_.release();
+    }
+  }
   for (int d = 0; d < 3; ++d) nf[d] = 1;
   for (int d = 0; d < dim; ++d) {
     int64_t n1;
@@ -253,7 +269,7 @@ void Engine<T>::setpts_type3(int64_t M_, const T *x, const T *y, const T *z, int
 
   // inner type-2 plan on the nf grid (setpts.hpp:286-319); one vector at a time
   EngineOpts io        = opts;
-  io.upsampfac         = sigma;
+  io.upsampfac         = opts.auto_sigma ? 0.0 : sigma;
   io.spreadinterponly  = 0;
   io.modeord           = 0;
   io.maxbatch          = 1;

@@ -45,9 +45,12 @@ def _dtypes(dtype):
 
 
 class _PlanCommon:
-    def info(self):
+    def info(self, inner=False):
+        """What the plan decided; inner=True: the inner type-2 plan of a type-3 plan (after
+        setpts)."""
         out = _lib.PlanInfo()
-        _check(self._lib.b200_get_plan_info(self._plan, C.byref(out)), "plan_info")
+        get = self._lib.b200_get_inner_plan_info if inner else self._lib.b200_get_plan_info
+        _check(get(self._plan, C.byref(out)), "plan_info")
         d = self.dim
         return dict(ns=out.ns, nc=out.nc, sigma=out.sigma, beta=out.beta, tol=out.tol,
                     nf=[out.nf[i] for i in range(d)], ms=[out.ms[i] for i in range(d)],

@@ -18,6 +18,8 @@ typedef struct b200_plan_info {
 } b200_plan_info;
 
 int b200_get_plan_info(void *plan, b200_plan_info *out);
+/* type-3 plans after setpts: the inner type-2 plan (its sigma, width, grid); error 13 otherwise */
+int b200_get_inner_plan_info(void *plan, b200_plan_info *out);
 /* sort permutation (sorted position -> user index), M entries, to HOST memory */
 int b200_get_sort_permutation(void *plan, uint32_t *host_out);
 /* the order the kernels work in, as setpts left it on the device: bins ascending, inside a bin
@@ -51,6 +53,14 @@ double b200_host_smallest_sigma(double tol, int dim, int type, int is_float, dou
 int b200_host_sigma_feasible(double sigma, double tol, int dim, int type, int is_float, double maxN);
 double b200_host_choose_sigma(double tol, int dim, int type, int is_float, const int64_t *modes,
                               double npoints);
+/* the candidate (sigma, ns) pairs the sigma search scores, in the reference's order
+ * (include/finufft/heuristics.hpp:82-107; smax = 2.5 gives the reference's own set), and the
+ * type-3 pick for nsources sources / ntargets targets with half-widths X[dim], S[dim]
+ * (heuristics.hpp:130-150, applied at setpts when finufft_opts.upsampfac = 0) */
+int b200_host_sigma_candidates(double tol, int dim, int type, int is_float, double maxN,
+                               double smax, double *sigma_out, int *ns_out, int cap);
+double b200_host_choose_sigma_type3(double tol, int dim, int is_float, double nsources,
+                                    double ntargets, const double *X, const double *S);
 int b200_host_fseries(int64_t nf, int ns, int nc, int is_float, const void *coef, void *out);
 /* library build tag, e.g. "finufft_b200 0.1 sm_100a" */
 const char *b200_version(void);

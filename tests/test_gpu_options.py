@@ -203,3 +203,66 @@ def test_auto_upsampfac_host_api(cuda, oracle, prec, tol, dim, modes, M):
         assert e_gpu <= max(2 * tol, 1.5 * e_ref), (type_, sigma, e_gpu, e_ref)
         hp.destroy()
         op.destroy()
+
+
+@pytest.mark.parametrize("prec,tol,dim,M,N,S", [
+    ("d", 1e-9, 2, 1500, 1200, 150.0),     # few points, wide frequency box: the FFTs dominate
+    ("f", 1e-4, 3, 1000, 900, 40.0),
+    ("d", 1e-6, 1, 800, 700, 3000.0),
+    ("d", 1e-9, 1, 300_000, 250_000, 30.0),  # many points on a short grid: sigma stays 2
+])
+def test_type3_auto_upsampfac_host_api(cuda, oracle, prec, tol, dim, M, N, S):
+    """Type 3 with finufft_opts.upsampfac = 0 on the host API: sigma3 is chosen at setpts from
+    the half-widths and the point counts, and the inner type-2 plan chooses its own sigma from its
+    grid and the number of targets (reference include/finufft/setpts.hpp:186-200, 302-304,
+    heuristics.hpp:130-150).  The kernel is rebuilt for the chosen sigma; results against the
+    direct sum (the reference's own dirft when the snapshot carries it) at the tolsweep-style bar
+    of the fixed-sigma test, for the forward and the adjoint transform, and against the
+    reference library run in ITS automatic mode (which picks sigma with its CPU cost model)."""
+    import finufft_b200 as F
+    rt, ct = (np.float32, np.complex64) if prec == "f" else (np.float64, np.complex128)
+    rng = np.random.default_rng(70 + dim)
+    pts = [rng.uniform(-np.pi, np.pi, M).astype(rt) + rt(0.2 * d) for d in range(dim)]
+    frq = [(rng.uniform(-S, S, N) + 0.1 * S * (d + 1)).astype(rt) for d in range(dim)]
+    c = _rand_c(rng, (M,), ct)
+    hp = F.HostPlan(3, dim, 1, tol, 1, ct, allow_eps_too_small=1)   # upsampfac = 0
+    assert hp.info()["sigma"] == 2.0                                  # until setpts
+    hp.setpts(*pts, **dict(zip("stu", frq)))
+    outer, inner = hp.info(), hp.info(inner=True)
+    # the pick is one of the candidates of the reference's minimiser (or the default 2.0)
+    lib = F.load()
+    cs, cn = (C.c_double * 32)(), (C.c_int * 32)()
+    t = float(np.float32(tol)) if prec == "f" else tol
+    n = lib.b200_host_sigma_candidates(t, dim, 3, int(prec == "f"), 1.0, 2.0, cs, cn, 32)
+    assert outer["sigma"] == 2.0 or any(
+        abs(outer["sigma"] - cs[i]) < 1e-12 and outer["ns"] == cn[i] for i in range(n)), outer
+    if M < 10_000:
+        assert 1.15 <= outer["sigma"] < 2.0 and 1.15 <= inner["sigma"] < 2.0, (outer, inner)
+    else:
+        assert outer["sigma"] == 2.0
+    # the inner type 2 transforms the outer grid
+    assert inner["ms"] == outer["nf"]
+    got = hp.execute(c)
+    lp, lf = pts[::-1] + [None] * (3 - dim), frq[::-1] + [None] * (3 - dim)
+    ds = oracle.dirft(3, lp[0], lp[1], lp[2], c.astype(np.complex128), 1,
+                      s=lf[0], t=lf[1], u=lf[2])
+    e_gpu = oracle.relerr(got, ds)
+    print(f"\n[type 3 auto: sigma3 {outer['sigma']:.4f} ns {outer['ns']} nf {outer['nf']}, "
+          f"inner sigma {inner['sigma']:.4f} ns {inner['ns']}] gpu-vs-direct {e_gpu:.2e}")
+    assert e_gpu <= 10 * tol
+    F_in = _rand_c(rng, (N,), ct)
+    adj = hp.execute_adjoint(F_in)
+    dsa = oracle.dirft(3, lf[0], lf[1], lf[2], F_in.astype(np.complex128), -1,
+                       s=lp[0], t=lp[1], u=lp[2])
+    assert oracle.relerr(adj, dsa) <= 10 * tol
+    if oracle.have_reference():
+        op = oracle.RefPlan(3, [1] * dim, 1, 1, tol, rt, sigma=0.0, dim=dim, nthr=4)
+        op.setpts(lp[0], lp[1], lp[2], lf[0], lf[1], lf[2])
+        want = op.execute(c)
+        e_ref = oracle.relerr(want, ds)
+        print(f"[reference auto] vs direct {e_ref:.2e}; gpu-vs-reference "
+              f"{oracle.relerr(got, want):.2e}")
+        assert oracle.relerr(got, want) <= 10 * tol
+        assert e_gpu <= max(2 * tol, 3 * e_ref)
+        op.destroy()
+    hp.destroy()

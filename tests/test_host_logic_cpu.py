@@ -107,6 +107,70 @@ def test_auto_upsampfac_search_matches_reference():
     assert lib.b200_host_choose_sigma(1e-9, 2, 1, 0, modes2, 1e7) == 2.0     # C4
 
 
+def test_sigma_candidates_are_the_reference_minimisers(tmp_path):
+    """The (sigma, ns) candidates the automatic-upsampfac search scores, for types 1, 2 and 3,
+    against a trace of the reference's own minimiser (include/finufft/heuristics.hpp:82-107,
+    called through oracle/_ref with a cost functor that records its arguments): same count, same
+    order, sigma equal to 1e-9.  The widths agree except where the reference evaluates its width
+    law exactly on the edge of its ceil() (its candidates are built to sit there) and rounding
+    puts it one wider; ours sit one part in 1e12 above the edge and get the intended width."""
+    import ctypes as C
+    import itertools
+    import finufft_b200
+    lib = finufft_b200.load()
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libfinufft_ref.so")
+    if not os.path.exists(ref_path):
+        pytest.skip("oracle/_ref/libfinufft_ref.so not built (no /root/reference)")
+    ref = C.CDLL(ref_path)
+    ref.ref_minimize_trace.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_double,
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
+    ncases = nlists = 0
+    for tol, dim, typ, isf, N in itertools.product(
+            (1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-9, 1e-12, 1e-14), (1, 2, 3), (1, 2, 3), (0, 1),
+            (1.0, 64.0, 512.0, 1e4, 1e6)):
+        if (typ == 3) != (N == 1.0) or (isf and tol < 1e-6):
+            continue
+        if isf:
+            tol = float(np.float32(tol))    # the plan holds tol in its own precision
+        a, an = (C.c_double * 32)(), (C.c_int * 32)()
+        b, bn = (C.c_double * 32)(), (C.c_int * 32)()
+        na = lib.b200_host_sigma_candidates(tol, dim, typ, isf, N, 2.5, a, an, 32)
+        nb = ref.ref_minimize_trace(tol, dim, typ, isf, N, b, bn, 32)
+        assert na == nb, (tol, dim, typ, isf, N, list(a[:na]), list(b[:nb]))
+        for i in range(na):
+            assert abs(a[i] - b[i]) < 1e-9 and bn[i] - an[i] in (0, 1), \
+                (tol, dim, typ, isf, N, i, a[i], an[i], b[i], bn[i])
+        assert an[0] == bn[0]
+        ncases += 1
+        nlists += na
+    assert ncases > 300 and nlists > 2 * ncases
+
+
+def test_type3_auto_upsampfac_choice():
+    """Type 3 with finufft_opts.upsampfac = 0: sigma3 is picked at setpts from the half-widths
+    and the point counts (include/finufft/setpts.hpp:186-200, heuristics.hpp:130-150) with this
+    device's cost model.  Checks of the pick itself: always a member of the candidate set or 2.0,
+    feasible; few points on a wide grid (FFT-dominated) go below 2; many points on a small grid
+    (spread-dominated) keep 2."""
+    import ctypes as C
+    import finufft_b200
+    lib = finufft_b200.load()
+    D3 = C.c_double * 3
+    for isf, tol in ((1, 1e-5), (0, 1e-9), (0, 1e-12)):
+        for dim in (1, 2, 3):
+            for M, N, X, S in ((1e3, 1e3, 3.0, 400.0), (1e7, 1e7, 3.14, 100.0), (1e8, 1e3, 1.0, 8.0)):
+                s = lib.b200_host_choose_sigma_type3(tol, dim, isf, M, N, D3(X, X, X), D3(S, S, S))
+                cs, cn = (C.c_double * 32)(), (C.c_int * 32)()
+                t = float(np.float32(tol)) if isf else tol
+                n = lib.b200_host_sigma_candidates(t, dim, 3, isf, 1.0, 2.0, cs, cn, 32)
+                assert s == 2.0 or any(abs(s - cs[i]) < 1e-12 for i in range(n)), (isf, tol, dim, s)
+                assert lib.b200_host_sigma_feasible(s, tol, dim, 3, isf, 1.0)
+    # 1e3 points against a 3D grid of ~ (2*2*400*3/pi)^3 cells: the FFT is everything
+    assert lib.b200_host_choose_sigma_type3(1e-9, 3, 0, 1e3, 1e3, D3(3, 3, 3), D3(400, 400, 400)) < 1.5
+    # 1e8 sources spread onto a grid of a few dozen cells per dimension: the spread is everything
+    assert lib.b200_host_choose_sigma_type3(1e-5, 3, 1, 1e8, 1e3, D3(1, 1, 1), D3(8, 8, 8)) == 2.0
+
+
 def test_bench_input_streams_are_the_reference_perftest_streams(tmp_path):
     """tools/perfdata.py (bench inputs) against the reference's own generator compiled from where
     it lies (perftest/randunif.h:29-73), when /root/reference is present; always: determinism,
