@@ -358,15 +358,14 @@ template<class T> int host_execute(void *plan, void *c, void *fk, bool adjoint) 
       }
     } drain{st, p->s_in, p->s_out};
     const int ngrp      = p->eng.point_groups();
-    const int64_t glen  = ngrp > 1 ? p->eng.group_len() : M;
     const int batch     = p->eng.batch;
     const int nbatches  = (ntr + batch - 1) / batch;
     // event slots: [0] start, then one per point unit (v, k), then one per mode batch
     auto ev_pts  = [&](int v, int k) { return p->event(1 + (size_t)v * ngrp + k); };
     auto ev_mode = [&](int b) { return p->event(1 + (size_t)ntr * ngrp + b); };
     auto pt_range = [&](int v, int k, int64_t &off, int64_t &cnt) {
-      const int64_t a = std::min<int64_t>(M, (int64_t)k * glen);
-      const int64_t e = ngrp > 1 ? std::min<int64_t>(M, (int64_t)(k + 1) * glen) : M;
+      const int64_t a = ngrp > 1 ? p->eng.group_begin(k) : 0;
+      const int64_t e = ngrp > 1 ? p->eng.group_begin(k + 1) : M;
       off = (int64_t)v * M + a;
       cnt = e - a;
     };

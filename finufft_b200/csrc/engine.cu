@@ -138,6 +138,15 @@ Engine<T>::Engine(int type_, int dim_, const int64_t *nmodes, int iflag, int ntr
   if (const char *env = getenv("B200_NUFFT_STAGE")) opts.stage = atoi(env);
   if (const char *env = getenv("B200_NUFFT_PRUNE")) opts.prune = atoi(env);
   if (const char *env = getenv("B200_NUFFT_PART")) opts.partition = atoi(env);
+  if (const char *env = getenv("B200_NUFFT_GROUP_FRACS")) {  // "0.1,0.3,0.3,0.3"
+    int j = 0;
+    for (const char *q = env; *q && j < 8; ++j) {
+      char *end = nullptr;
+      opts.group_frac[j] = strtod(q, &end);
+      if (end == q) break;
+      q = *end == ',' ? end + 1 : end;
+    }
+  }
   plan_kernel();
   if (type != 3) {
     for (int d = 0; d < dim; ++d) ms[d] = nmodes[d];
@@ -386,12 +395,28 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
   {
     uint32_t k = (uint32_t)want_groups_;
     if (type == 3 || M < 2 * (int64_t)k || (uint64_t)geom.nbins1 * k > 0x7fffffffull) k = 1;
-    geom.nchunks   = k;
-    // equal groups: sizes shrinking geometrically towards the last group (so that the spread no
-    // upload hides is short) were measured slower at C3, 22.0 -> 24.2 ms (ratio 0.65) and
-    // 23.1 ms (0.8), type 2 25.8 -> 27.5 ms (profiles/r2_e2e_group_layouts.txt)
-    geom.chunk_len = k > 1 ? (uint32_t)((M + k - 1) / k) : 0xffffffffu;
-    geom.nbins     = geom.nbins1 * k;
+    geom.nchunks = k;
+    geom.nbins   = geom.nbins1 * k;
+    // Group sizes (fractions of the points); measured at C3 through the host API
+    // (profiles/r2_e2e_group_layouts.txt).  Type 2: the download of group k runs under the
+    // interpolation of group k+1 and the LAST download under nothing, so a smaller last group
+    // shortens the step (24.9 -> 23.9 ms).  Type 1: every layout tried (small first group,
+    // small last group, 3 / 4 / 5 groups) is equal to or slower than equal groups (21.6 ms).
+    double frac[GridGeom<T>::kMaxGroups];
+    for (uint32_t j = 0; j < k; ++j) frac[j] = 1.0 / k;
+    if (type == 2 && k == 4) frac[0] = 0.30, frac[1] = 0.30, frac[2] = 0.25, frac[3] = 0.15;
+    if (opts.group_frac[0] > 0.0)
+      for (uint32_t j = 0; j < k; ++j) frac[j] = std::max(opts.group_frac[j], 1e-3);
+    double tot = 0.0, acc = 0.0;
+    for (uint32_t j = 0; j < k; ++j) tot += frac[j];
+    for (int j = 0; j < GridGeom<T>::kMaxGroups - 1; ++j) geom.gb[j] = 0xffffffffu;
+    uint32_t prev = 0;
+    for (uint32_t j = 0; j + 1 < k; ++j) {
+      acc += frac[j];
+      uint32_t b = (uint32_t)std::llround((double)M * acc / tot);
+      b          = std::min<uint32_t>(std::max<uint32_t>(b, prev + 1), (uint32_t)M - (k - 1 - j));
+      geom.gb[j] = prev = b;
+    }
   }
   xs_.alloc(M);
   if (dim > 1) ys_.alloc(M);
@@ -401,7 +426,8 @@ template<class T> void Engine<T>::sort_points(const T *x, const T *y, const T *z
   if (unsorted_) {
     // the caller asked for no sort: identity permutation (reference indexSort,
     // spreadinterp.hpp:186-191), coordinates kept as given, point-driven kernels at execute
-    geom.nchunks = 1, geom.chunk_len = 0xffffffffu, geom.nbins = geom.nbins1;
+    geom.nchunks = 1, geom.nbins = geom.nbins1;
+    for (int j = 0; j < GridGeom<T>::kMaxGroups - 1; ++j) geom.gb[j] = 0xffffffffu;
     swept_ = swept2_ = staged_ = radix_order_ = part_used_ = false;
     nsub = 0, nitems_ = 0;
     group_sub_.assign(2, 0);

@@ -43,6 +43,7 @@ struct EngineOpts {
   int sweep            = 1;     // 3D float: tube-sweep kernels (0 = generic kernels)
   int stage            = -1;    // two-level strength permutation (stage.cuh): -1 auto, 0 off, 1 on
   int check_sigma      = 0;     // host (finufft_*) entry points apply the CPU feasibility rule
+  double group_frac[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // debugging aid: sizes of the point groups
   int auto_sigma       = 0;     // upsampfac = 0 on the host API: choose sigma at setpts (types 1, 2)
   int partition        = 1;     // setpts: 1 partition sort where it pays, 2 always, 0 counting sort
   // bin sort at setpts: 1 sort, 0 keep the user's order and run the point-driven kernels
@@ -98,10 +99,15 @@ template<class T> class Engine {
               const T *u);
   void execute(C *c, C *fk, bool adjoint, const ExecHooks *hooks = nullptr);
   // split the next setpts into k groups of consecutive user indices (types 1 and 2 only)
-  void set_point_groups(int k) { want_groups_ = k < 1 ? 1 : (k > 16 ? 16 : k); }
+  void set_point_groups(int k) {
+    want_groups_ = k < 1 ? 1 : (k > GridGeom<T>::kMaxGroups ? GridGeom<T>::kMaxGroups : k);
+  }
   int point_groups() const { return (int)geom.nchunks; }
+  // user indices [group_begin(k), group_begin(k+1)) form group k of the last setpts
+  int64_t group_begin(int k) const {
+    return k <= 0 ? 0 : (k >= (int)geom.nchunks ? M : (int64_t)geom.gb[k - 1]);
+  }
   const Engine<T> *inner() const { return inner_.get(); }  // type 3: the inner type-2 plan
-  int64_t group_len() const { return (int64_t)geom.chunk_len; }
 
   // ---- introspection (tests, benches) ----
   int type, dim, ntr, sign;

@@ -59,7 +59,7 @@ __device__ __forceinline__ uint32_t bin_key_of(T x, T y, T z, uint32_t i, const 
     key += (uint32_t)g.nb[0] * (uint32_t)g.nb[1] *
            (uint32_t)(int)mul_rn(fold_rescale<T>(z, g.nf_t[2]), (T)(1.0 / kBinZ));
   key = key < g.nbins1 ? key : g.nbins1 - 1;  // only non-finite input can trip this
-  if (g.nchunks > 1) key += (i / g.chunk_len) * g.nbins1;  // group-major (sort.cuh)
+  if (g.nchunks > 1) key += point_group(g, i) * g.nbins1;  // group-major (sort.cuh)
   return key;
 }
 

@@ -365,7 +365,7 @@ k_bin_count(const T *__restrict__ x, const T *__restrict__ y, const T *__restric
       if (DIM > 2) pz = z[i];
     }
     uint32_t key = valid ? bin_key<T, DIM>(px, py, pz, g) : 0xffffffffu;
-    if (valid && g.nchunks > 1) key += (i / g.chunk_len) * g.nbins1;  // group-major (sort.cuh)
+    if (valid && g.nchunks > 1) key += point_group(g, i) * g.nbins1;  // group-major (sort.cuh)
     // one atomic per distinct bin in the warp
     const uint32_t peers = __match_any_sync(0xffffffffu, key);
     const int leader     = __ffs(peers) - 1;

@@ -20,13 +20,17 @@ template<class T> struct GridGeom {
   T nf_t[3];      // the same, converted to T the way the CPU code does (T(N))
   int nb[3];      // bins per dim
   uint32_t nbins; // sort bins in total = nbins1 * nchunks
-  // Host-pointer plans may split the points into nchunks groups of chunk_len consecutive USER
-  // indices (capi.cu: the strengths of group k arrive while group k-1 is being spread).  The
-  // sort key is then group-major: key = group * nbins1 + bin, every group a complete bin-sorted
-  // point set of its own; kernels recover the bin with a modulo.
-  uint32_t nbins1    = 0;  // bins of the grid = nb[0]*nb[1]*nb[2]
-  uint32_t nchunks   = 1;
-  uint32_t chunk_len = 0xffffffffu;
+  // Host-pointer plans may split the points into nchunks groups of consecutive USER indices
+  // (capi.cu: the strengths of group k arrive while group k-1 is being spread).  The sort key is
+  // then group-major: key = group * nbins1 + bin, every group a complete bin-sorted point set of
+  // its own; kernels recover the bin with a modulo.  Group k holds the user indices
+  // [gb[k-1], gb[k]) (gb[-1] = 0); the groups need not be equal (engine.cu: sort_points);
+  // unused entries are 0xffffffff.
+  uint32_t nbins1  = 0;  // bins of the grid = nb[0]*nb[1]*nb[2]
+  uint32_t nchunks = 1;
+  static constexpr int kMaxGroups = 8;
+  uint32_t gb[kMaxGroups - 1] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu,
+                                 0xffffffffu, 0xffffffffu, 0xffffffffu};
   // z window (3D, sharded plans: slab.cu): the grid array holds only zwin_n consecutive planes
   // of the periodic nf[2]-plane grid, starting at global plane zwin_org.  Folding, bins and
   // stencils stay those of the whole grid; a cell of global plane P lives in array plane
@@ -34,6 +38,15 @@ template<class T> struct GridGeom {
   // touches.  zwin_n = 0: the array is the whole grid.
   int zwin_org = 0, zwin_n = 0;
 };
+
+// group of user index i (call only when g.nchunks > 1)
+template<class T>
+__host__ __device__ __forceinline__ uint32_t point_group(const GridGeom<T> &g, uint32_t i) {
+  uint32_t k = 0;
+#pragma unroll
+  for (int j = 0; j < GridGeom<T>::kMaxGroups - 1; ++j) k += i >= g.gb[j] ? 1u : 0u;
+  return k;
+}
 
 // array plane of global plane gz (already wrapped into [0, nf[2])), or -1 outside the window
 template<class T> __host__ __device__ __forceinline__ int grid_plane(const GridGeom<T> &g, int gz) {

@@ -209,7 +209,7 @@ def test_auto_upsampfac_host_api(cuda, oracle, prec, tol, dim, modes, M):
     ("d", 1e-9, 2, 1500, 1200, 150.0),     # few points, wide frequency box: the FFTs dominate
     ("f", 1e-4, 3, 1000, 900, 40.0),
     ("d", 1e-6, 1, 800, 700, 3000.0),
-    ("d", 1e-9, 1, 300_000, 250_000, 30.0),  # many points on a short grid: sigma stays 2
+    ("d", 1e-9, 1, 40_000, 30_000, 30.0),    # many points on a short grid: sigma stays 2
 ])
 def test_type3_auto_upsampfac_host_api(cuda, oracle, prec, tol, dim, M, N, S):
     """Type 3 with finufft_opts.upsampfac = 0 on the host API: sigma3 is chosen at setpts from
