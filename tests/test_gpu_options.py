@@ -142,7 +142,13 @@ def test_oneshot_finufftf3d3_and_1d1(cuda, oracle):
     vp = C.c_void_p
     f.argtypes = [C.c_int64, vp, vp, vp, vp, C.c_int, C.c_float, C.c_int64, vp, vp, vp, vp, vp]
     p = lambda a: a.ctypes.data_as(vp)  # noqa: E731
-    assert f(M, p(x), p(y), p(z), p(c), 1, tol, N, p(s), p(t), p(u), p(fk), None) in (0, 1)
+    # explicit upsampfac: with opts = NULL (upsampfac = 0) both libraries would pick sigma with
+    # their own cost models (test_type3_auto_upsampfac_host_api covers that); this test is about
+    # the wrapper, so both run at sigma = 2
+    o = F._lib.FinufftOpts()
+    lib.finufftf_default_opts(C.byref(o))
+    o.upsampfac = 2.0
+    assert f(M, p(x), p(y), p(z), p(c), 1, tol, N, p(s), p(t), p(u), p(fk), C.byref(o)) in (0, 1)
     op = _checker(oracle)(3, [1, 1, 1], 1, 1, tol, np.float32, nthr=4, dim=3)
     op.setpts(x, y, z, s, t, u)
     assert oracle.relerr(fk, op.execute(c)) <= 2 * tol
@@ -209,7 +215,7 @@ def test_auto_upsampfac_host_api(cuda, oracle, prec, tol, dim, modes, M):
     ("d", 1e-9, 2, 1500, 1200, 150.0),     # few points, wide frequency box: the FFTs dominate
     ("f", 1e-4, 3, 1000, 900, 40.0),
     ("d", 1e-6, 1, 800, 700, 3000.0),
-    ("d", 1e-9, 1, 40_000, 30_000, 30.0),    # many points on a short grid: sigma stays 2
+    ("d", 1e-9, 1, 12_000, 10_000, 30.0),    # many points on a short grid: sigma stays 2
 ])
 def test_type3_auto_upsampfac_host_api(cuda, oracle, prec, tol, dim, M, N, S):
     """Type 3 with finufft_opts.upsampfac = 0 on the host API: sigma3 is chosen at setpts from
