@@ -1,5 +1,5 @@
 """CPU-only, world_size 2 over gloo: the z-slab sharding of one 3D transform
-(finufft_b200/zslab.py) — slab ownership, ghost-plane ring exchange, slab->pencil all_to_all,
+(tests/zslab_model.py, the host-side model of csrc/slab.cu) — slab ownership, ghost-plane ring exchange, slab->pencil all_to_all,
 mode selection and deconvolution — with the CPU oracle standing in for the GPU spreader /
 interpolator.  The sharded result must equal the oracle's unsharded transform."""
 import os
@@ -13,13 +13,14 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 MODES = (16, 12, 10)   # python order (ms3, ms2, ms1)
 TOL = 1e-9
 
 
 def test_mode_indices_and_bounds():
-    from finufft_b200.zslab import mode_indices, slab_bounds, split_even
+    from zslab_model import mode_indices, slab_bounds, split_even
     ix, ak = mode_indices(20, 7)            # k = -3..3
     assert ix.tolist() == [17, 18, 19, 0, 1, 2, 3] and ak.tolist() == [3, 2, 1, 0, 1, 2, 3]
     ix, ak = mode_indices(16, 8)            # k = -4..3
@@ -64,7 +65,7 @@ def _worker(rank, world, port, type_, q):
     from oracle import build as ob
     ob.build_oracle()
     from oracle import oracle as O
-    from finufft_b200.zslab import SlabPlan, route_points, slab_of_points
+    from zslab_model import SlabPlan, route_points, slab_of_points
     M = 3000
     z, y, x = _points(M)
     rng = np.random.default_rng(6)

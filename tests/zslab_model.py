@@ -1,4 +1,5 @@
-"""HOST-SIDE MODEL of the z-slab decomposition, kept for the CPU tests only.
+"""TEST INFRASTRUCTURE: host-side model of the z-slab decomposition, for the CPU tests only
+(tests/test_zslab_gloo_cpu.py); not part of the finufft_b200 package.
 
 The product path is csrc/slab.cu behind include/b200_sharded.h (python: finufft_b200.sharded.
 ShardedPlan): C++ driving the library's own kernels, cuFFT and NCCL.  This module restates the
@@ -79,7 +80,7 @@ class SlabPlan:
                  make_local=None, device=None, upsampfac=2.0):
         import torch
         import torch.distributed as dist
-        from . import hostmath
+        from finufft_b200 import hostmath
         if nufft_type not in (1, 2) or len(n_modes) != 3:
             raise ValueError("SlabPlan handles 3D transforms of type 1 and 2")
         self.torch, self.dist, self.group = torch, dist, group
@@ -116,7 +117,7 @@ class SlabPlan:
         self.dec = 1.0 / (self.phi[0][:, None, None] * self.phi[1][None, self.y_lo:self.y_hi, None]
                           * self.phi[2][None, None, :])
         if make_local is None:
-            from .plan import Plan
+            from finufft_b200.plan import Plan
 
             def make_local(shape):
                 return Plan(nufft_type, shape, 1, eps, self.isign,
