@@ -517,7 +517,9 @@ def main():
                             "ms_per_step": e2e_ms,
                             "api": "b200_slab[f]_execute: pinned host -> device copy of the "
                                    "rank's input, sharded execute, device -> host of its output"},
-                    "gpu_launches": launches,
+                    # this library's own kernels launched inside the timed region (cuFFT's and
+                    # memsets not counted), this rank
+                    "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
                     "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved,
                                  "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                                  "traffic": None, "peak_source": peak_kind,
@@ -681,7 +683,9 @@ def main():
                             "d2h_bytes_per_step": int(np.prod(out_shape)) * cbytes * (1 if batched or world == 1 else world),
                             "ms_per_step": e2e_ms, "steps": e2e_steps,
                             "api": "finufft[f]_execute (host pointers, pinned buffers)"},
-                    "gpu_launches": launches,
+                    # this library's own kernels launched inside the timed region (cuFFT's and
+                    # memsets not counted), this rank
+                    "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
                     "roofline": roofline, "cpu_baseline": cpu,
                     "stages_ms": stage_avg, "setpts_ms": setpts_ms,
                     "setpts_wall_ms": setpts_wall_ms,
